@@ -1,0 +1,105 @@
+"""Pins oracle/bin_oracle.py to the fixtures produced by the unmodified reference
+(oracle/make_golden.py).  fp32 CPU both sides -> tolerance 2e-6 (accumulation-order noise)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bin_oracle as O
+
+TOL = 2e-6
+
+
+def _load(golden_dir, name):
+    return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, name)).items()}
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return O.synth_state_dict(0)
+
+
+def test_schema(sd):
+    assert len(sd) == 1332
+    uniq = {t.data_ptr(): t for t in sd.values()}
+    assert len(uniq) == 540
+    assert sum(t.numel() for t in uniq.values()) == 11_441_668
+
+
+@pytest.mark.parametrize("tag", ["window_a", "window_b"])
+def test_window(golden_dir, sd, tag):
+    g = _load(golden_dir, tag + ".npz")
+    B, H, W, smooth, seed, _ = [int(v) for v in g["meta"]]
+    fr = O.synth_frames(6, B, H, W, seed=seed, smooth=bool(smooth))
+    outs = O.window_forward(fr, sd)
+    assert len(outs) == 14
+    for k, o in enumerate(outs):
+        assert (o - g[f"out{k}"]).abs().max().item() <= TOL, k
+
+
+def test_pyramid(golden_dir, sd):
+    g = _load(golden_dir, "pyramid.npz")
+    fr = O.synth_frames(5, 1, 16, 24, seed=77)
+    prev = [t * 2 - 1 for t in O.synth_frames(6, 1, 16, 24, seed=78)]
+    msd = O.sub_sd(sd, "model")
+    for tag, p in (("none", [None] * 6), ("prev", prev)):
+        outs = O.pyramid(fr, p, msd)
+        for k, o in enumerate(outs):
+            assert (o - g[f"{tag}{k}"]).abs().max().item() <= TOL, (tag, k)
+
+
+@pytest.mark.parametrize("name,n", [("model1_1", 2), ("model2_1", 3), ("model3_1", 5), ("model4_1", 5)])
+def test_backbone(golden_dir, sd, name, n):
+    g = _load(golden_dir, f"backbone_{name}.npz")
+    fr = O.synth_frames(n, 2, 20, 36, seed=100 + n)
+    y = O.backbone(fr, O.sub_sd(sd, "model." + name))
+    assert (y - g["out"]).abs().max().item() <= TOL
+
+
+def test_rdb(golden_dir, sd):
+    g = _load(golden_dir, "rdb.npz")
+    bsd = O.sub_sd(sd, "model.model2_1")
+    y = O.rdb(g["x"], bsd, "RDBs.3")
+    assert (y - g["out"]).abs().max().item() <= 1e-5      # inputs are N(0,1): larger magnitudes
+    c0 = torch.cat((g["x"], torch.relu(O.conv(g["x"], bsd, "RDBs.3.convs.0.conv.0"))), 1)
+    assert (c0 - g["conv0"]).abs().max().item() <= 1e-5
+
+
+def test_pixel_reshuffle(golden_dir):
+    g = _load(golden_dir, "pixel_reshuffle.npz")
+    assert torch.equal(O.space_to_depth2(g["x"]), g["out"])
+
+
+def test_convlstm(golden_dir, sd):
+    g = _load(golden_dir, "convlstm.npz")
+    h, (c, _) = O.convlstm(g["x"], sd, "clstm_7_prime_prime", None)
+    assert (h - g["h_none"]).abs().max().item() <= TOL and (c - g["c_none"]).abs().max().item() <= TOL
+    h, (c, _) = O.convlstm(g["x"], sd, "clstm_7_prime_prime", (g["c0"], g["h0"]))
+    assert (h - g["h_state"]).abs().max().item() <= TOL and (c - g["c_state"]).abs().max().item() <= TOL
+
+
+def test_window_grad(golden_dir, sd):
+    """Backward of the oracle (autograd through the restatement) against the reference's autograd."""
+    g = _load(golden_dir, "window_grad.npz")
+    names = [k[2:] for k in g if k.startswith("d:")]
+    sd2 = dict(sd)
+    leaves = {}
+    for n in names:                       # aliases share storage: make the canonical tensor a leaf everywhere
+        leaf = sd[n].clone().requires_grad_(True)
+        leaves[n] = leaf
+        for k, v in sd.items():
+            if v.data_ptr() == sd[n].data_ptr():
+                sd2[k] = leaf
+    fr = [f.requires_grad_(True) for f in O.synth_frames(6, 1, 16, 16, seed=9)]
+    outs = O.window_forward(fr, sd2)
+    cots = O.synth_frames(14, 1, 16, 16, seed=10)
+    loss = sum((o * (c - 0.5)).sum() for o, c in zip(outs, cots))
+    assert abs(loss.item() - g["loss"].item()) <= 1e-3 * max(1.0, abs(g["loss"].item()))
+    grads = torch.autograd.grad(loss, fr + [leaves[n] for n in names])
+    for k in range(6):
+        ref = g[f"dframe{k}"]
+        assert (grads[k] - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()), k
+    for n, gr in zip(names, grads[6:]):
+        ref = g["d:" + n]
+        assert (gr - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()), n
