@@ -1,0 +1,98 @@
+"""ctypes binding of libbin_b200.so (include/bin_b200.h).  Fails loudly when the CUDA
+library is missing -- there is no CPU or PyTorch fallback on the product path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbin_b200.so")
+
+BIN_MAX_CALLS = 5
+BIN_MAX_FRAMES = 5
+BIN_BACKBONE_NCONV = 66
+EPI_P8, EPI_PIXSHUF, EPI_FINAL = 0, 1, 2
+
+
+class Act(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("B", C.c_int), ("planes", C.c_int), ("H", C.c_int), ("W", C.c_int)]
+
+
+class Frames(C.Structure):
+    _fields_ = [("frame", (C.c_void_p * BIN_MAX_FRAMES) * BIN_MAX_CALLS),
+                ("out", C.c_void_p * BIN_MAX_CALLS),
+                ("ncalls", C.c_int), ("nframes", C.c_int), ("Bc", C.c_int)]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [("in0", Act), ("in0_plane0", C.c_int), ("in0_planes", C.c_int),
+                ("in1", Act), ("in1_plane0", C.c_int), ("in1_planes", C.c_int),
+                ("w_packed", C.c_void_p), ("bias", C.c_void_p),
+                ("ksize", C.c_int), ("cout_pad", C.c_int), ("relu", C.c_int), ("epilogue", C.c_int), ("variant", C.c_int),
+                ("out", Act), ("out_plane0", C.c_int),
+                ("res", Act), ("res_plane0", C.c_int),
+                ("fr", Frames)]
+
+
+class Net(C.Structure):
+    _fields_ = [("blob", C.c_void_p * 4), ("lstm_w", C.c_void_p * 6), ("lstm_b", C.c_void_p * 6)]
+
+
+class BinB200Error(RuntimeError):
+    pass
+
+
+_SIGS = {
+    "bin_abi_version": (C.c_int, []),
+    "bin_last_error": (C.c_char_p, []),
+    "bin_check_device": (C.c_int, []),
+    "bin_nchw_to_p8": (C.c_int, [C.c_void_p, C.c_int, Act, C.c_int, C.c_void_p]),
+    "bin_p8_to_nchw": (C.c_int, [Act, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "bin_pack_frames": (C.c_int, [C.POINTER(Frames), C.c_int, C.c_int, Act, C.c_void_p]),
+    "bin_packed_weight_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "bin_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "bin_conv_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "bin_convlstm_fwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 3 + [C.c_void_p]),
+    "bin_backbone_packed_bytes": (C.c_size_t, [C.c_int]),
+    "bin_backbone_pack": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "bin_backbone_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "bin_backbone_fwd": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(Frames), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "bin_rdb_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                              C.c_void_p, C.c_size_t, C.c_void_p]),
+    "bin_window_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
+    "bin_window_fwd": (C.c_int, [C.POINTER(Net), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "bin_pyramid3_fwd": (C.c_int, [C.POINTER(Net), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                   C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "bin_microbench_mma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BinB200Error(
+                f"{LIB_PATH} not found: build it with `python -m bin_b200.build` (nvcc, sm_100a). "
+                "bin_b200 has no CPU/PyTorch fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)          # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        if L.bin_abi_version() != 1:
+            raise BinB200Error("libbin_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise BinB200Error(f"bin_b200 error {code}: {lib().bin_last_error().decode()}")
+
+
+def exported_symbols():
+    return list(_SIGS.keys())

@@ -1,0 +1,320 @@
+// bin_b200 -- memory-bound helper kernels: layout conversion, input packer (space-to-depth),
+// weight packer, ConvLSTM cell, and the tcgen05 issue-rate microbenchmark.
+#include "common.cuh"
+#include "internal.h"
+
+namespace binb {
+
+// ------------------------------------------------------------------ fp32 NCHW <-> P8 fp16
+__global__ void nchw_to_p8_kernel(const float* __restrict__ x, int C, __half* __restrict__ dst, int planes,
+                                  int plane0, int nplanes, int B, int H, int W) {
+  const size_t total = (size_t)B * nplanes * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xw = i % W;
+    const int y = (i / W) % H;
+    const int pl = (i / ((size_t)W * H)) % nplanes;
+    const int b = i / ((size_t)W * H * nplanes);
+    __align__(16) __half v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = pl * 8 + e;
+      v[e] = __float2half_rn(c < C ? x[(((size_t)b * C + c) * H + y) * W + xw] : 0.f);
+    }
+    const size_t off = ((((size_t)b * planes + plane0 + pl) * H + y) * W + xw) * 8;
+    *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+__global__ void p8_to_nchw_kernel(const __half* __restrict__ src, int planes, int plane0, int C,
+                                  float* __restrict__ y_out, int B, int H, int W) {
+  const size_t total = (size_t)B * C * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xw = i % W;
+    const int y = (i / W) % H;
+    const int c = (i / ((size_t)W * H)) % C;
+    const int b = i / ((size_t)W * H * C);
+    const size_t off = ((((size_t)b * planes + plane0 + (c >> 3)) * H + y) * W + xw) * 8 + (c & 7);
+    y_out[i] = __half2float(src[off]);
+  }
+}
+
+// ------------------------------------------------------------------ K3: frame concat + space-to-depth + cast
+// Reference: RDN.py:211/269/323 torch.cat(frames,1) then pixel_reshuffle(.,2) (RDN.py:107-132):
+// packed channel = (f*3+rgb)*4 + dy*2 + dx for pixel (2y+dy, 2x+dx); zero-padded to dst.planes*8.
+__global__ void pack_frames_kernel(const __grid_constant__ bin_frames_t fr, int H, int W, __half* __restrict__ dst,
+                                   int planes) {
+  const int h = H / 2, w = W / 2;
+  const int Btot = fr.ncalls * fr.Bc;
+  const size_t total = (size_t)Btot * planes * h * w;
+  const int cin = 12 * fr.nframes;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = i % w;
+    const int y = (i / w) % h;
+    const int pl = (i / ((size_t)w * h)) % planes;
+    const int b = i / ((size_t)w * h * planes);
+    const int call = b / fr.Bc, bb = b % fr.Bc;
+    __align__(16) __half v[8];
+#pragma unroll
+    for (int half8 = 0; half8 < 2; ++half8) {          // 4 packed channels = one (frame, rgb) 2x2 patch
+      const int c4 = pl * 2 + half8;                   // index of the (f,rgb) pair
+      if (c4 * 4 < cin) {
+        const int f = c4 / 3, rgb = c4 % 3;
+        const float* src = fr.frame[call][f] + (((size_t)bb * 3 + rgb) * H + 2 * y) * W + 2 * x;
+        const float2 r0 = *reinterpret_cast<const float2*>(src);
+        const float2 r1 = *reinterpret_cast<const float2*>(src + W);
+        v[half8 * 4 + 0] = __float2half_rn(r0.x);
+        v[half8 * 4 + 1] = __float2half_rn(r0.y);
+        v[half8 * 4 + 2] = __float2half_rn(r1.x);
+        v[half8 * 4 + 3] = __float2half_rn(r1.y);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[half8 * 4 + e] = __float2half_rn(0.f);
+      }
+    }
+    const size_t off = ((((size_t)b * planes + pl) * h + y) * w + x) * 8;
+    *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// ------------------------------------------------------------------ weight packer
+// OIHW fp32 -> [nh][chunk][ky][kx][4][NT][8] fp16, or (stackx) [chunk][ky][4][kx*cout_pad+co][8]
+__global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, int ks, int cout_pad, int cin_pad,
+                                   int nt, int stackx, __half* __restrict__ dst) {
+  const size_t total = (size_t)cout_pad * cin_pad * ks * ks;
+  const int nchunks = cin_pad / kKC;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t t = i;
+    int e, kp, kx, ky, ch, co;
+    e = t % 8; t /= 8;
+    if (stackx) {
+      const int n = t % (ks * cout_pad); t /= (ks * cout_pad);
+      kx = n / cout_pad; co = n % cout_pad;
+      kp = t % kKPL; t /= kKPL;
+      ky = t % ks; t /= ks;
+      ch = (int)t;
+    } else {
+      const int n = t % nt; t /= nt;
+      kp = t % kKPL; t /= kKPL;
+      kx = t % ks; t /= ks;
+      ky = t % ks; t /= ks;
+      ch = t % nchunks; t /= nchunks;
+      co = (int)t * nt + n;
+    }
+    const int ci = ch * kKC + kp * 8 + e;
+    float v = 0.f;
+    if (co < cout && ci < cin) v = w[(((size_t)co * cin + ci) * ks + ky) * ks + kx];
+    dst[i] = __float2half_rn(v);
+  }
+}
+
+__global__ void pack_bias_kernel(const float* __restrict__ b, int cout, int cout_pad, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cout_pad) dst[i] = i < cout ? b[i] : 0.f;
+}
+
+// ------------------------------------------------------------------ K5: ConvLSTMCell (RDN.py:50-95)
+__global__ void convlstm_kernel(const float* __restrict__ x, const float* __restrict__ c_prev,
+                                const float* __restrict__ h_prev, const float* __restrict__ w,
+                                const float* __restrict__ bias, float* __restrict__ h_out, float* __restrict__ c_out,
+                                int B, int H, int W) {
+  __shared__ float sw[12 * 6 * 9];
+  __shared__ float sb[12];
+  for (int i = threadIdx.x; i < 12 * 6 * 9; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 12) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const size_t hw = (size_t)H * W;
+  const size_t total = (size_t)B * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xw = i % W;
+    const int y = (i / W) % H;
+    const int b = i / hw;
+    float g[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) g[k] = sb[k];
+    const int nin = h_prev ? 6 : 3;                         // h = 0 contributes nothing (RDN.py:57-68)
+    for (int c = 0; c < nin; ++c) {
+      const float* src = (c < 3 ? x + ((size_t)b * 3 + c) * hw : h_prev + ((size_t)b * 3 + (c - 3)) * hw);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = xw + kx - 1;
+          if (xx < 0 || xx >= W) continue;
+          const float v = src[(size_t)yy * W + xx];
+#pragma unroll
+          for (int k = 0; k < 12; ++k) g[k] = fmaf(sw[(k * 6 + c) * 9 + ky * 3 + kx], v, g[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {                            // i,j,f,o = chunk(4) (RDN.py:79)
+      const float gi = g[c], gj = g[3 + c], gf = g[6 + c], go = g[9 + c];
+      const float cp = c_prev ? c_prev[((size_t)b * 3 + c) * hw + (size_t)y * W + xw] : 0.f;
+      const float si = 1.f / (1.f + expf(-gi));
+      const float sf = 1.f / (1.f + expf(-(gf + 1.0f)));   // forget_bias = 1.0 (RDN.py:16,81)
+      const float so = 1.f / (1.f + expf(-go));
+      const float cn = cp * sf + si * tanhf(gj);
+      const float hn = tanhf(cn) * so;
+      const size_t off = ((size_t)b * 3 + c) * hw + (size_t)y * W + xw;
+      h_out[off] = hn;
+      if (c_out) c_out[off] = cn;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ tcgen05 issue-rate microbenchmark
+// mode bits: [0,4) independent accumulators cycled round-robin; [4,6) A layout; [6,8) B layout
+// (0 = no-swizzle K-major, 1 = SWIZZLE_128B, 2 = SWIZZLE_64B, 3 = SWIZZLE_32B); bit 8: shift the A
+// start by one row per MMA; bit 9: M=64 instead of 128.  Operand contents are zeros (timing only).
+__device__ __forceinline__ uint64_t bench_desc(uint32_t addr, int layout, uint32_t noswz_lbo) {
+  uint64_t d = (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 46);
+  if (layout == 0) {
+    d |= (uint64_t)((noswz_lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(128 >> 4) << 32;
+  } else {
+    const uint32_t sbo = layout == 1 ? 1024 : layout == 2 ? 512 : 256;
+    const uint64_t type = layout == 1 ? 2 : layout == 2 ? 4 : 6;
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= type << 61;
+  }
+  return d;
+}
+__global__ void __launch_bounds__(128, 1) mma_bench_kernel(int n, int iters, int mode, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (threadIdx.x < 32) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base_s;
+  if (threadIdx.x < 32) {                     // whole warp converged; one elected lane issues
+    const int M = (mode & 0x200) ? 64 : 128;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 48 * 1024);
+    int nacc = mode & 0xf;
+    if (nacc < 1) nacc = 1;
+    if (nacc * n > 512) nacc = 512 / n;
+    const int la = (mode >> 4) & 3, lb = (mode >> 6) & 3;
+    const bool shift = (mode & 0x100) != 0;
+    const uint32_t row16 = (la == 0 ? 16 : la == 1 ? 128 : la == 2 ? 64 : 32) >> 4;
+    const uint64_t ad0 = bench_desc(a0, la, 320 * 16);
+    const uint64_t bd0 = bench_desc(b0, lb, (uint32_t)n * 16);
+    const uint32_t dstep = (nacc > 1) ? (uint32_t)n : 0u;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 8) {
+      if (elect_one()) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint64_t ad = ad0 + (shift ? (uint64_t)(u * row16) : 0ull);
+          umma_f16_ss(tb + (uint32_t)(u % 2) * dstep, ad, bd0, idesc, 1u);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    tmem_dealloc(tb, 512);
+  }
+}
+
+// ------------------------------------------------------------------ launch wrappers
+static inline int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+int launch_nchw_to_p8(const float* x, int C, const bin_act_t& dst, int plane0, cudaStream_t s) {
+  const int nplanes = (C + 7) / 8;
+  if (plane0 + nplanes > dst.planes) return fail(BIN_ERR_ARG, "nchw_to_p8: plane range exceeds tensor");
+  const size_t total = (size_t)dst.B * nplanes * dst.H * dst.W;
+  nchw_to_p8_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, C, (__half*)dst.ptr, dst.planes, plane0, nplanes, dst.B,
+                                                         dst.H, dst.W);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_p8_to_nchw(const bin_act_t& src, int plane0, int C, float* y, cudaStream_t s) {
+  if (plane0 + (C + 7) / 8 > src.planes) return fail(BIN_ERR_ARG, "p8_to_nchw: plane range exceeds tensor");
+  const size_t total = (size_t)src.B * C * src.H * src.W;
+  p8_to_nchw_kernel<<<grid_for(total, 256), 256, 0, s>>>((const __half*)src.ptr, src.planes, plane0, C, y, src.B,
+                                                         src.H, src.W);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_pack_frames(const bin_frames_t& fr, int H, int W, const bin_act_t& dst, cudaStream_t s) {
+  if ((H & 1) || (W & 1)) return fail(BIN_ERR_ARG, "frame height/width must be even (pixel_reshuffle, RDN.py:123-128)");
+  if (fr.ncalls < 1 || fr.ncalls > BIN_MAX_CALLS || fr.nframes < 1 || fr.nframes > BIN_MAX_FRAMES)
+    return fail(BIN_ERR_ARG, "pack_frames: bad frame table");
+  if (dst.B != fr.ncalls * fr.Bc || dst.H != H / 2 || dst.W != W / 2 || dst.planes * 8 < 12 * fr.nframes)
+    return fail(BIN_ERR_ARG, "pack_frames: destination geometry mismatch");
+  const size_t total = (size_t)dst.B * dst.planes * dst.H * dst.W;
+  pack_frames_kernel<<<grid_for(total, 256), 256, 0, s>>>(fr, H, W, (__half*)dst.ptr, dst.planes);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_pack_weight(const float* w, int cout, int cin, int ks, int cout_pad, int cin_pad, int variant,
+                       void* packed, cudaStream_t s) {
+  if (cin_pad % kKC || cout_pad % 16 || cout > cout_pad || cin > cin_pad)
+    return fail(BIN_ERR_ARG, "pack_conv_weight: cin_pad must be a multiple of 32, cout_pad of 16");
+  const int nt = conv_nt(cout_pad);
+  if (cout_pad % nt) return fail(BIN_ERR_ARG, "pack_conv_weight: cout_pad must be <=128 or a multiple of 128");
+  const size_t total = (size_t)cout_pad * cin_pad * ks * ks;
+  const int stackx = (ks == 3 && cout_pad == 32 && variant == BIN_CONV_DEFAULT) ? 1 : 0;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, cout, cin, ks, cout_pad, cin_pad, nt, stackx,
+                                                          (__half*)packed);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_pack_bias(const float* b, int cout, int cout_pad, float* dst, cudaStream_t s) {
+  pack_bias_kernel<<<(cout_pad + 127) / 128, 128, 0, s>>>(b, cout, cout_pad, dst);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_convlstm(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
+                    float* h_out, float* c_out, int B, int H, int W, cudaStream_t s) {
+  if ((c_prev == nullptr) != (h_prev == nullptr)) return fail(BIN_ERR_ARG, "convlstm: give both c_prev and h_prev or neither");
+  const size_t total = (size_t)B * H * W;
+  convlstm_kernel<<<grid_for(total, 128), 128, 0, s>>>(x, c_prev, h_prev, w, b, h_out, c_out, B, H, W);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int run_mma_bench(int n, int iters, int mode, float* cycles_host) {
+  if (n < 16 || n > 256 || n % 16) return fail(BIN_ERR_ARG, "microbench: N must be a multiple of 16 in [16,256]");
+  long long* d = nullptr;
+  const int grid = 148;
+  BIN_CUDA_OK(cudaMalloc(&d, grid * sizeof(long long)));
+  BIN_CUDA_OK(cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  mma_bench_kernel<<<grid, 128, 96 * 1024>>>(n, iters, mode, d);
+  BIN_CUDA_OK(cudaGetLastError());
+  BIN_CUDA_OK(cudaDeviceSynchronize());
+  long long h[148];
+  BIN_CUDA_OK(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  long long mx = 0;
+  for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
+  *cycles_host = (float)mx / (float)iters;
+  return BIN_OK;
+}
+
+}  // namespace binb

@@ -1,0 +1,485 @@
+// bin_b200 -- implicit-GEMM convolution for sm_100a (tcgen05.mma + TMEM + TMA).
+//
+// Replaces every nn.Conv2d on the BIN hot path (reference models/archs/RDN.py:141,162,187-188,
+// 199-200,205,207 and the 36/60-channel twins): stride 1, zero padding k/2, bias, optional ReLU
+// (RDN.py:142), optional residual (RDN.py:165,219), PixelShuffle(2) folded into the store
+// (RDN.py:206) or the final "+ mean(input frames)" fp32 NCHW store (RDN.py:221,279,333).
+//
+// GEMM view: M = pixels, N = Cout, K = taps x Cin.  Activations are P8 fp16
+// [B][C/8][H][W][8]: one pixel of one 8-channel plane is exactly one 16-byte row of a UMMA
+// K-major / no-swizzle core matrix, and pixels are contiguous, so the A operand of tap (ky,kx)
+// is the SAME shared-memory tile addressed through a descriptor whose start is shifted by
+// (ky*32+kx)*16 bytes -- no im2col, the halo tile is fetched once per 32-channel chunk by one
+// 5-D TMA box load whose out-of-bounds zero fill implements the conv's zero padding.
+// Tile: 8 rows x 32-pixel smem pitch = 256 GEMM rows = two 128xN fp32 accumulators in TMEM;
+// the 2*PAD right-most columns of each row are junk rows that are never stored.
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer (activation box + weight slab per stage, mbarrier ring)
+//   warp 1 lane 0 : tcgen05.mma issuer (accumulates taps x k-steps into TMEM)
+//   warp 2        : TMEM allocator
+//   warps 4..7    : epilogue (tcgen05.ld -> bias/ReLU/residual -> 128-bit fp16 stores),
+//                   double-buffered against the next tile's MMAs through tmem_full/empty.
+// Weight sets that fit (RDB convs, LFF, SFENet2, GFF.1, UPNet.2) stay resident in shared memory.
+#include <stdio.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace binb {
+
+// SX ("stack x"): the KS horizontal taps are folded into the GEMM N dimension -- B rows are
+// (kx, cout), the A operand is NOT shifted in x, and the epilogue adds the kx-th column group of
+// the accumulator row of pixel p+kx (a warp shuffle: each epilogue warp holds exactly one 32-pixel
+// tile row, and the lanes that would need the next row are the junk columns).  One MMA then does
+// 128 x (KS*NT) x 16 instead of 128 x NT x 16 for the same 4 KB A read, which lifts the Cout=32
+// RDB convs from 40 % to 86 % of the shared-memory-bound tcgen05 issue rate
+// (measured: MMA(128xNx16) costs max(N/2, 32+N/4) cycles).
+template <int NT, int KS, bool SX>
+struct ConvCfg {
+  static constexpr int PAD = KS / 2;
+  static constexpr int TW = kTWH - 2 * PAD;              // valid output columns per tile
+  static constexpr bool ROWSPLIT = (KS == 5);            // 5x5: one stage per (chunk, ky)
+  static constexpr int ROWS = ROWSPLIT ? kTH : kTH + 2 * PAD;
+  static constexpr int A_PLANE = ROWS * kTWH * 16;       // bytes of one plane of a stage
+  static constexpr int A_BYTES = kKPL * A_PLANE;
+  static constexpr int NMMA = SX ? NT * KS : NT;         // N of one tcgen05.mma
+  static constexpr int TAPS_C = SX ? KS : KS * KS;       // B slabs ("taps") per chunk
+  static constexpr int TAPS_S = (SX || ROWSPLIT) ? KS : KS * KS;  // taps per stage
+  static constexpr int NSUB = ROWSPLIT ? KS : 1;         // stages per chunk
+  static constexpr int W_TAP = kKPL * NMMA * 16;         // bytes per tap per chunk
+  static constexpr int W_STAGE = TAPS_S * W_TAP;
+  static constexpr int W_CHUNK = TAPS_C * W_TAP;
+  static constexpr int ACC_COLS = kMT * NMMA;
+  static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64
+                                   : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
+  static_assert(2 * ACC_COLS <= 512, "TMEM overflow");
+  static_assert(!(SX && ROWSPLIT), "SX is only used for 3x3");
+  static_assert(NMMA % 16 == 0 && NMMA <= 256, "invalid UMMA N");
+};
+
+struct Ctrl {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t wfull[kMaxResidentChunks];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Ctrl) <= 1024, "ctrl block");
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+  __half2 h = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(h);
+}
+
+template <int NT, int KS, int EPI, bool SX>
+__global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  using C = ConvCfg<NT, KS, SX>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
+  float* sbias = reinterpret_cast<float*>(smem + 1024);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.nstages;
+  const int nchunks = p.nch0 + p.nch1;
+  const int stage_bytes = C::A_BYTES + (p.resident ? 0 : C::W_STAGE);
+  uint8_t* res_w = smem + kCtrlBytes;
+  uint8_t* stage0 = res_w + (p.resident ? nchunks * C::W_CHUNK : 0);
+
+  // ------------------------------------------------------------ one-time setup
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmap0);
+    if (p.nch1 > 0) tma_prefetch_desc(&p.tmap1);
+    for (int i = 0; i < kMaxStages; ++i) {
+      mbar_init(&ctrl->full[i], 1);
+      mbar_init(&ctrl->empty[i], 1);
+    }
+    for (int i = 0; i < kMaxResidentChunks; ++i) mbar_init(&ctrl->wfull[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctrl->tmem_full[i], 1);
+      mbar_init(&ctrl->tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < NT * p.nh; i += blockDim.x) sbias[i] = p.bias[i];
+  if (warp == 2) {
+    tmem_alloc(&ctrl->tmem_base, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    // ========================================================== TMA producer
+    if (p.resident) {
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_expect_tx(&ctrl->wfull[c], C::W_CHUNK);
+        bulk_load_1d(res_w + c * C::W_CHUNK, reinterpret_cast<const uint8_t*>(p.w) + (size_t)c * C::W_CHUNK,
+                     C::W_CHUNK, &ctrl->wfull[c]);
+      }
+    }
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      int t = tile;
+      const int nh = t % p.nh; t /= p.nh;
+      const int txi = t % p.tiles_x; t /= p.tiles_x;
+      const int tyi = t % p.tiles_y;
+      const int b = t / p.tiles_y;
+      const int x0 = txi * C::TW - C::PAD, y0 = tyi * kTH - C::PAD;
+      for (int c = 0; c < nchunks; ++c) {
+        const bool seg1 = c >= p.nch0;
+        const void* tmap = seg1 ? (const void*)&p.tmap1 : (const void*)&p.tmap0;
+        const int plane = seg1 ? p.plane0_1 + (c - p.nch0) * kKPL : p.plane0_0 + c * kKPL;
+        for (int sub = 0; sub < C::NSUB; ++sub, ++it) {
+          const uint32_t s = it % S, ph = (it / S) & 1;
+          mbar_wait(&ctrl->empty[s], ph ^ 1);
+          uint8_t* a_dst = stage0 + (size_t)s * stage_bytes;
+          mbar_expect_tx(&ctrl->full[s], stage_bytes);
+          tma_load_4d(a_dst, tmap, &ctrl->full[s], x0 * 8, y0 + (C::ROWSPLIT ? sub : 0), plane, b);
+          if (!p.resident) {
+            const size_t woff = ((size_t)(nh * nchunks + c) * C::TAPS_C + (C::ROWSPLIT ? sub * KS : 0)) * C::W_TAP;
+            bulk_load_1d(a_dst + C::A_BYTES, reinterpret_cast<const uint8_t*>(p.w) + woff, C::W_STAGE,
+                         &ctrl->full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ========================================================== MMA issuer (warp converged, one elected lane)
+    constexpr uint32_t idesc = umma_idesc_f16(128, C::NMMA);
+    constexpr uint32_t A_HI = (128u >> 4) | (1u << 14);            // SBO=128 B, descriptor version 1
+    constexpr uint32_t A_LBO = ((uint32_t)C::A_PLANE >> 4) << 16;
+    constexpr uint32_t B_LBO = ((uint32_t)(C::NMMA * 16) >> 4) << 16;
+    uint32_t it = 0, acc_it = 0;
+    bool first_tile = true;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++acc_it) {
+      const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+      mbar_wait(&ctrl->tmem_empty[as], aph ^ 1);
+      tc_fence_after();
+      for (int c = 0; c < nchunks; ++c) {
+        if (p.resident && first_tile) mbar_wait(&ctrl->wfull[c], 0);
+        for (int sub = 0; sub < C::NSUB; ++sub, ++it) {
+          const uint32_t s = it % S, ph = (it / S) & 1;
+          mbar_wait(&ctrl->full[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(stage0 + (size_t)s * stage_bytes);
+          const uint32_t w_base = p.resident
+                                      ? smem_u32(res_w + c * C::W_CHUNK) + (C::ROWSPLIT ? sub * KS * C::W_TAP : 0)
+                                      : a_base + C::A_BYTES;
+          const uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | A_LBO;
+          const uint32_t b_lo = ((w_base >> 4) & 0x3FFFu) | B_LBO;
+          const uint32_t not_first = (c | sub) != 0 ? 1u : 0u;
+          if (elect_one()) {
+#pragma unroll
+            for (int m = 0; m < kMT; ++m) {
+              const uint32_t d = tmem_base + as * C::ACC_COLS + m * C::NMMA;
+#pragma unroll
+              for (int tp = 0; tp < C::TAPS_S; ++tp) {
+                const int ky = SX ? tp : (C::ROWSPLIT ? 0 : tp / KS);
+                const int kx = SX ? 0 : (C::ROWSPLIT ? tp : tp % KS);
+                const uint32_t a_off = (uint32_t)(m * 128 + ky * kTWH + kx);   // in 16-byte rows
+#pragma unroll
+                for (int j = 0; j < kKC / 16; ++j) {
+                  const uint64_t ad = ((uint64_t)A_HI << 32) | (a_lo + a_off + j * 2 * (C::A_PLANE >> 4));
+                  const uint64_t bd = ((uint64_t)A_HI << 32) | (b_lo + (tp * C::W_TAP + j * 2 * C::NMMA * 16) / 16);
+                  umma_f16_ss(d, ad, bd, idesc, (tp == 0 && j == 0) ? not_first : 1u);
+                }
+              }
+            }
+            umma_commit(&ctrl->empty[s]);   // frees the smem stage once these MMAs retire
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one()) umma_commit(&ctrl->tmem_full[as]);  // accumulators of this tile complete
+      __syncwarp();
+      first_tile = false;
+    }
+  } else if (warp >= 4) {
+    // ========================================================== epilogue
+    const int q = warp & 3;
+    uint32_t acc_it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++acc_it) {
+      int t = tile;
+      const int nh = t % p.nh; t /= p.nh;
+      const int txi = t % p.tiles_x; t /= p.tiles_x;
+      const int tyi = t % p.tiles_y;
+      const int b = t / p.tiles_y;
+      const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+      // residual tile (RDN.py:165, :219) is independent of the accumulators: fetch it first so its
+      // global-load latency overlaps the MMAs instead of serialising the epilogue.
+      uint4 rbuf[(EPI == BIN_EPI_P8 && !SX) ? kMT * (NT / 8) : 1];
+      if constexpr (EPI == BIN_EPI_P8 && !SX) {
+        if (p.res != nullptr) {
+#pragma unroll
+          for (int m = 0; m < kMT; ++m) {
+            const int L = m * 128 + q * 32 + lane;
+            const int y = tyi * kTH + (L >> 5), x = txi * C::TW + (L & 31);
+            const bool valid = ((L & 31) < C::TW) && (y < p.H) && (x < p.W);
+#pragma unroll
+            for (int k = 0; k < NT / 8; ++k) {
+              const size_t off = ((((size_t)b * p.res_planes + p.res_plane0 + (nh * NT) / 8 + k) * p.H + y) * p.W + x) * 8;
+              rbuf[m * (NT / 8) + k] = valid ? *reinterpret_cast<const uint4*>(p.res + off) : make_uint4(0, 0, 0, 0);
+            }
+          }
+        }
+      }
+      mbar_wait(&ctrl->tmem_full[as], aph);
+      tc_fence_after();
+#pragma unroll
+      for (int m = 0; m < kMT; ++m) {
+        const int L = m * 128 + q * 32 + lane;
+        const int ty = L >> 5, tx = L & 31;
+        const int y = tyi * kTH + ty, x = txi * C::TW + tx;
+        const bool valid = (tx < C::TW) && (y < p.H) && (x < p.W);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + m * C::NMMA;
+        if constexpr (EPI == BIN_EPI_P8) {
+#pragma unroll
+          for (int n0 = 0; n0 < NT; n0 += 16) {
+            float f[16];
+            if constexpr (SX) {
+              // out[p] = D[p][kx=0] + D[p+1][kx=1] + D[p+2][kx=2]; p+1, p+2 are lanes +1, +2 of this warp
+              uint32_t v0[16], v1[16], v2[16];
+              tmem_ld16(taddr + n0, v0);
+              tmem_ld16(taddr + NT + n0, v1);
+              tmem_ld16(taddr + 2 * NT + n0, v2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), 1);
+                const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 2);
+                f[i] = ((__uint_as_float(v0[i]) + b1) + b2) + sbias[n0 + i];
+              }
+            } else {
+              uint32_t v[16];
+              tmem_ld16(taddr + n0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + sbias[nh * NT + n0 + i];
+            }
+            if (valid) {
+              if (p.relu) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+              }
+              const int cpl = (nh * NT + n0) >> 3;   // channel plane of f[0]
+              if (!SX && p.res != nullptr) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const uint4 r = rbuf[SX ? 0 : m * (NT / 8) + n0 / 8 + h];
+                  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 g = unpack_h2(rr[i]);
+                    f[h * 8 + 2 * i] += g.x;
+                    f[h * 8 + 2 * i + 1] += g.y;
+                  }
+                }
+              }
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint4 o;
+                o.x = pack_h2(f[h * 8 + 0], f[h * 8 + 1]);
+                o.y = pack_h2(f[h * 8 + 2], f[h * 8 + 3]);
+                o.z = pack_h2(f[h * 8 + 4], f[h * 8 + 5]);
+                o.w = pack_h2(f[h * 8 + 6], f[h * 8 + 7]);
+                const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + cpl + h) * p.H + y) * p.W + x) * 8;
+                *reinterpret_cast<uint4*>(p.out + off) = o;
+              }
+            }
+          }
+        } else if constexpr (EPI == BIN_EPI_PIXSHUF) {
+          // out[c, 2y+i, 2x+j] = conv[4c+2i+j, y, x]   (nn.PixelShuffle(2), RDN.py:206)
+#pragma unroll 1
+          for (int n0 = 0; n0 < NT; n0 += 32) {
+            uint32_t v0[16], v1[16];
+            tmem_ld16(taddr + n0, v0);
+            tmem_ld16(taddr + n0 + 16, v1);
+            tmem_ld_wait();
+            if (valid) {
+              float f[32];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                f[i] = __uint_as_float(v0[i]) + sbias[nh * NT + n0 + i];
+                f[16 + i] = __uint_as_float(v1[i]) + sbias[nh * NT + n0 + 16 + i];
+              }
+              const int opl = (nh * NT + n0) >> 5;   // output plane (8 channels = 32 conv channels)
+              const int H2 = 2 * p.H, W2 = 2 * p.W;
+#pragma unroll
+              for (int ij = 0; ij < 4; ++ij) {
+                uint4 o;
+                o.x = pack_h2(f[0 * 4 + ij], f[1 * 4 + ij]);
+                o.y = pack_h2(f[2 * 4 + ij], f[3 * 4 + ij]);
+                o.z = pack_h2(f[4 * 4 + ij], f[5 * 4 + ij]);
+                o.w = pack_h2(f[6 * 4 + ij], f[7 * 4 + ij]);
+                const int yy = 2 * y + (ij >> 1), xx = 2 * x + (ij & 1);
+                const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + opl) * H2 + yy) * W2 + xx) * 8;
+                *reinterpret_cast<uint4*>(p.out + off) = o;
+              }
+            }
+          }
+        } else {  // BIN_EPI_FINAL: fp32 NCHW = conv + bias + mean(frames)
+          uint32_t v[16];
+          tmem_ld16(taddr, v);
+          tmem_ld_wait();
+          if (valid) {
+            const int call = b / p.fr.Bc, bb = b % p.fr.Bc;
+            const size_t hw = (size_t)p.H * p.W;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const size_t off = ((size_t)bb * 3 + c) * hw + (size_t)y * p.W + x;
+              float acc = p.fr.frame[call][0][off];
+              for (int fi = 1; fi < p.fr.nframes; ++fi) acc += p.fr.frame[call][fi][off];
+              const float mean = acc / (float)p.fr.nframes;
+              p.fr.out[call][off] = (__uint_as_float(v[c]) + sbias[c]) + mean;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&ctrl->tmem_empty[as]);
+    }
+  }
+
+  // ------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+
+int make_p8_tmap(CUtensorMap* m, const bin_act_t& t, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(BIN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(t.ptr) & 15) != 0) return fail(BIN_ERR_ARG, "P8 tensor not 16-byte aligned");
+  // The (8 channels, W) dims of a P8 plane row are contiguous in memory, so they are described as ONE
+  // dimension of W*8 elements: the box row is then 32 px * 16 B = 512 contiguous bytes (a 16-byte
+  // inner box made the TMA unit the bottleneck).  OOB zero fill works per element, i.e. per pixel.
+  cuuint64_t dims[4] = {(cuuint64_t)t.W * 8, (cuuint64_t)t.H, (cuuint64_t)t.planes, (cuuint64_t)t.B};
+  cuuint64_t strides[3] = {(cuuint64_t)t.W * 16, (cuuint64_t)t.H * t.W * 16, (cuuint64_t)t.planes * t.H * t.W * 16};
+  cuuint32_t box[4] = {(cuuint32_t)kTWH * 8, (cuuint32_t)box_rows, (cuuint32_t)kKPL, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, t.ptr, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BIN_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return BIN_OK;
+}
+
+static int num_sms() {
+  static int n = []() {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+template <int NT, int KS, int EPI, bool SX>
+static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
+  using C = ConvCfg<NT, KS, SX>;
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  const int H = a.in0.H, W = a.in0.W, B = a.in0.B;
+  BIN_TRY(make_p8_tmap(&p.tmap0, a.in0, C::ROWS));
+  if (a.in1_planes > 0) {
+    if (a.in1.H != H || a.in1.W != W || a.in1.B != B) return fail(BIN_ERR_ARG, "in1 geometry differs from in0");
+    BIN_TRY(make_p8_tmap(&p.tmap1, a.in1, C::ROWS));
+  }
+  p.plane0_0 = a.in0_plane0; p.nch0 = a.in0_planes / kKPL;
+  p.plane0_1 = a.in1_plane0; p.nch1 = a.in1_planes / kKPL;
+  p.w = reinterpret_cast<const __half*>(a.w_packed);
+  p.bias = a.bias;
+  p.H = H; p.W = W; p.Btot = B;
+  p.tiles_x = (W + C::TW - 1) / C::TW;
+  p.tiles_y = (H + kTH - 1) / kTH;
+  p.nh = a.cout_pad / NT;
+  p.ntiles = B * p.tiles_x * p.tiles_y * p.nh;
+  p.relu = a.relu;
+  const int nchunks = p.nch0 + p.nch1;
+  // keep the whole weight set resident in smem when it leaves room for >= 3 activation stages
+  p.resident = (p.nh == 1 && nchunks <= kMaxResidentChunks &&
+                kCtrlBytes + nchunks * C::W_CHUNK + 3 * C::A_BYTES + 256 <= kSmemMax) ? 1 : 0;
+  const int res_bytes = p.resident ? nchunks * C::W_CHUNK : 0;
+  const int stage_bytes = C::A_BYTES + (p.resident ? 0 : C::W_STAGE);
+  int S = (kSmemMax - kCtrlBytes - res_bytes - 256) / stage_bytes;
+  if (S > kMaxStages) S = kMaxStages;
+  if (S < 2) return fail(BIN_ERR_UNSUPPORTED, "conv configuration does not fit in shared memory");
+  p.nstages = S;
+  const int smem_bytes = kCtrlBytes + res_bytes + S * stage_bytes + 256;
+  p.out = reinterpret_cast<__half*>(a.out.ptr); p.out_planes = a.out.planes; p.out_plane0 = a.out_plane0;
+  p.res = reinterpret_cast<const __half*>(a.res.ptr); p.res_planes = a.res.planes; p.res_plane0 = a.res_plane0;
+  p.fr = a.fr;
+  auto kern = conv_igemm_kernel<NT, KS, EPI, SX>;
+  static bool attr_done = false;   // per instantiation; idempotent, so a benign race at worst
+  if (!attr_done) {
+    BIN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    attr_done = true;
+  }
+  int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
+  if (grid < 1) return BIN_OK;
+  kern<<<grid, 256, smem_bytes, s>>>(p);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+
+int launch_conv(const bin_conv_args_t& a, cudaStream_t s) {
+  if (a.in0_planes % kKPL || a.in1_planes % kKPL || a.in0_planes <= 0)
+    return fail(BIN_ERR_ARG, "input plane counts must be positive multiples of 4 (32 channels)");
+  if (a.in0_plane0 + a.in0_planes > a.in0.planes || (a.in1_planes > 0 && a.in1_plane0 + a.in1_planes > a.in1.planes))
+    return fail(BIN_ERR_ARG, "input plane range exceeds tensor");
+  if (a.epilogue == BIN_EPI_P8) {
+    if (a.out.H != a.in0.H || a.out.W != a.in0.W || a.out.B != a.in0.B ||
+        a.out_plane0 + a.cout_pad / 8 > a.out.planes)
+      return fail(BIN_ERR_ARG, "output tensor geometry mismatch");
+    if (a.res.ptr && (a.res.H != a.in0.H || a.res.W != a.in0.W || a.res.B != a.in0.B ||
+                      a.res_plane0 + a.cout_pad / 8 > a.res.planes))
+      return fail(BIN_ERR_ARG, "residual tensor geometry mismatch");
+    if (a.ksize == 3 && a.cout_pad == 32 && a.variant == 0) return launch_inst<32, 3, BIN_EPI_P8, true>(a, s);
+    if (a.ksize == 3 && a.cout_pad == 32 && a.variant == 1) return launch_inst<32, 3, BIN_EPI_P8, false>(a, s);
+    if (a.ksize == 3 && a.cout_pad == 96) return launch_inst<96, 3, BIN_EPI_P8, false>(a, s);
+    if (a.ksize == 5 && a.cout_pad == 96) return launch_inst<96, 5, BIN_EPI_P8, false>(a, s);
+    if (a.ksize == 1 && a.cout_pad == 96) return launch_inst<96, 1, BIN_EPI_P8, false>(a, s);
+  } else if (a.epilogue == BIN_EPI_PIXSHUF) {
+    if (a.out.H != 2 * a.in0.H || a.out.W != 2 * a.in0.W || a.out.B != a.in0.B ||
+        a.out_plane0 + a.cout_pad / 32 > a.out.planes)
+      return fail(BIN_ERR_ARG, "pixel-shuffle output geometry mismatch");
+    if (a.ksize == 3 && a.cout_pad == 256) return launch_inst<128, 3, BIN_EPI_PIXSHUF, false>(a, s);
+  } else if (a.epilogue == BIN_EPI_FINAL) {
+    if (a.fr.ncalls < 1 || a.fr.ncalls > BIN_MAX_CALLS || a.fr.nframes < 1 || a.fr.nframes > BIN_MAX_FRAMES ||
+        a.fr.ncalls * a.fr.Bc != a.in0.B)
+      return fail(BIN_ERR_ARG, "frame table does not match the batch");
+    if (a.ksize == 3 && a.cout_pad == 16) return launch_inst<16, 3, BIN_EPI_FINAL, false>(a, s);
+  }
+  return fail(BIN_ERR_UNSUPPORTED, "no kernel instantiation for this conv (ksize/cout_pad/epilogue)");
+}
+
+}  // namespace binb

@@ -1,0 +1,57 @@
+// bin_b200 internal declarations shared by the .cu files (not part of the ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../include/bin_b200.h"
+
+namespace binb {
+
+// ------------------------------------------------------------------ errors
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+#define BIN_CUDA_OK(expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::binb::fail(BIN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+#define BIN_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != BIN_OK) return _r; \
+  } while (0)
+
+// ------------------------------------------------------------------ tile geometry of the conv kernel
+constexpr int kTWH = 32;   // smem row pitch of an activation tile, in pixels (= 4 UMMA row groups)
+constexpr int kTH = 8;     // output rows per CTA tile
+constexpr int kMT = 2;     // 128-row accumulators per CTA tile (kTH*kTWH/128)
+constexpr int kKC = 32;    // input channels per pipeline stage
+constexpr int kKPL = 4;    // P8 planes per stage
+constexpr int kCtrlBytes = 2048;
+constexpr int kSmemMax = 227 * 1024;
+constexpr int kMaxStages = 8;
+constexpr int kMaxResidentChunks = 8;
+
+struct alignas(64) ConvParams {
+  CUtensorMap tmap0, tmap1;
+  int plane0_0, nch0, plane0_1, nch1;  // segment start plane / number of 32-channel chunks
+  const __half* w;
+  const float* bias;
+  int H, W, Btot;                      // conv resolution
+  int tiles_x, tiles_y, ntiles, nh;    // nh = cout_pad / NT
+  int relu, resident, nstages;
+  __half* out; int out_planes, out_plane0;
+  const __half* res; int res_planes, res_plane0;
+  bin_frames_t fr;
+};
+
+int launch_conv(const bin_conv_args_t& a, cudaStream_t s);
+
+// packed-weight geometry
+inline int conv_nt(int cout_pad) { return cout_pad > 128 ? 128 : cout_pad; }
+
+}  // namespace binb

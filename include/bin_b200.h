@@ -1,0 +1,147 @@
+/* bin_b200 -- C ABI of the B200-native BIN hot path (libbin_b200.so).
+ *
+ * The reference (laomao0/BIN) has no FFI layer: its boundary for this path is the Python
+ * nn.Module contract reached through models/networks.py:9-10 -> models/archs/RDN.py:469-471
+ * (SURVEY.md 8b).  This header is the "thin C-ABI extension" north_star asks for: every
+ * entry point replaces one reference symbol (cited per function) and is called by the
+ * Python mirror in bin_b200/rdn.py through ctypes.  Conventions:
+ *   - all data pointers are DEVICE pointers unless the name ends in _host;
+ *   - every call is asynchronous on the given CUDA stream (cudaStream_t passed as void*);
+ *   - return 0 on success, non-zero error code otherwise; bin_last_error() gives the text
+ *     (thread-local, valid until the next failing call on that thread);
+ *   - no allocation inside: callers pass workspaces sized by the *_bytes() queries;
+ *   - no global mutable state: re-entrant per (device, stream).
+ *
+ * Device layouts
+ *   frames / outputs : fp32 NCHW, exactly what the reference module takes and returns.
+ *   "planar-8" (P8)  : fp16 activations [B][C/8][H][W][8]  (8-channel planes; one pixel of one
+ *                      plane = 16 B = one UMMA core-matrix row, so any pixel shift of a smem
+ *                      tile is a 16-byte descriptor offset -> implicit GEMM without im2col).
+ *   packed conv W    : fp16 [Cin_pad/32][kh][kw][4][Cout_pad][8]  (K-major B operand, one
+ *                      contiguous slab per 32-channel K chunk), + fp32 bias[Cout_pad].
+ *                      3x3 convs with Cout=32 (the RDB convs, 70 % of all FLOPs) use the
+ *                      "x-stacked" layout [Cin_pad/32][kh][4][kw*32+cout][8]: the three horizontal
+ *                      taps become GEMM columns (N=96) and are re-aligned in the epilogue.
+ */
+#ifndef BIN_B200_H_
+#define BIN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BIN_ABI_VERSION 1
+#define BIN_MAX_CALLS 5   /* same-weight backbone calls batched along N */
+#define BIN_MAX_FRAMES 5  /* frames per backbone call (2, 3 or 5) */
+
+enum { BIN_OK = 0, BIN_ERR_ARG = 1, BIN_ERR_CUDA = 2, BIN_ERR_UNSUPPORTED = 3, BIN_ERR_WORKSPACE = 4 };
+
+typedef void* bin_stream_t; /* cudaStream_t */
+
+int bin_abi_version(void);
+const char* bin_last_error(void);
+/* 0 if the current device is sm_100 (B200) and the driver exposes cuTensorMapEncodeTiled. */
+int bin_check_device(void);
+
+/* ---- P8 activation tensor view ------------------------------------------------------- */
+typedef struct {
+  void* ptr; /* fp16 [B][planes][H][W][8] */
+  int B, planes, H, W;
+} bin_act_t;
+
+/* ---- frame pointer table (one row per batched backbone call) --------------------------- */
+typedef struct {
+  const float* frame[BIN_MAX_CALLS][BIN_MAX_FRAMES]; /* each (Bc,3,H,W) fp32 NCHW */
+  float* out[BIN_MAX_CALLS];                          /* each (Bc,3,H,W) fp32 NCHW */
+  int ncalls, nframes, Bc;
+} bin_frames_t;
+
+/* ---- layout helpers (tests, boundary) ----------------------------------------------- */
+/* fp32 NCHW (B,C,H,W) -> P8 planes [plane0, plane0+ceil(C/8)); channels past C are zeroed. */
+int bin_nchw_to_p8(const float* x, int C, bin_act_t dst, int plane0, bin_stream_t s);
+/* P8 planes -> fp32 NCHW (B,C,H,W). */
+int bin_p8_to_nchw(bin_act_t src, int plane0, int C, float* y, bin_stream_t s);
+
+/* RDN.py:107-132 pixel_reshuffle(cat(frames),2) fused with the fp32->fp16 cast and channel
+ * padding: dst is P8 (ncalls*Bc, cin_pad/8, H/2, W/2); channel (f*3+rgb)*4 + dy*2+dx. */
+int bin_pack_frames(const bin_frames_t* fr, int H, int W, bin_act_t dst, bin_stream_t s);
+
+/* ---- weights ------------------------------------------------------------------------- */
+size_t bin_packed_weight_bytes(int cout_pad, int cin_pad, int ksize);
+/* nn.Conv2d weight (cout,cin,k,k) fp32 OIHW -> packed fp16; rows/cols past cout/cin are zero. */
+/* variant: BIN_CONV_DEFAULT, or BIN_CONV_PLAIN to force the un-stacked layout for 3x3/Cout=32. */
+int bin_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int cout_pad, int cin_pad, int variant,
+                         void* packed, bin_stream_t s);
+
+/* ---- the implicit-GEMM convolution (tcgen05) ------------------------------------------ */
+enum { BIN_EPI_P8 = 0, BIN_EPI_PIXSHUF = 1, BIN_EPI_FINAL = 2 };
+enum { BIN_CONV_DEFAULT = 0, BIN_CONV_PLAIN = 1 };
+typedef struct {
+  /* input channels = planes [in0_plane0, +in0_planes) of in0 followed by planes of in1
+   * (dense concat without a copy: RDN.py:147 torch.cat((x,out),1)); plane counts multiples of 4. */
+  bin_act_t in0; int in0_plane0, in0_planes;
+  bin_act_t in1; int in1_plane0, in1_planes; /* in1_planes = 0 -> unused */
+  const void* w_packed; const float* bias;   /* bias: fp32[cout_pad] */
+  int ksize;     /* 1, 3 or 5; stride 1, zero padding ksize/2 (all convs of RDN.py) */
+  int cout_pad;  /* 16, 32, 96 or 256 */
+  int relu;      /* RDN.py:142 */
+  int epilogue;  /* BIN_EPI_* */
+  int variant;   /* BIN_CONV_*; must match the variant the weights were packed with */
+  /* BIN_EPI_P8: out planes [out_plane0, +cout_pad/8), optional residual (RDN.py:165, :219) */
+  bin_act_t out; int out_plane0;
+  bin_act_t res; int res_plane0; /* res.ptr = NULL -> none */
+  /* BIN_EPI_PIXSHUF (RDN.py:206): cout_pad=256 -> out is P8 (B, 8 planes, 2H, 2W) */
+  /* BIN_EPI_FINAL (RDN.py:207 + :221/:279/:333): cout_pad=16 (3 used); out = conv + bias +
+   * mean(frames) written as fp32 NCHW to fr.out[call] */
+  bin_frames_t fr;
+} bin_conv_args_t;
+int bin_conv_fwd(const bin_conv_args_t* a, bin_stream_t s);
+
+/* ---- ConvLSTMCell.forward, RDN.py:50-95 ------------------------------------------------ */
+/* x,(c_prev,h_prev): (B,3,H,W) fp32; c_prev/h_prev NULL = zeros (RDN.py:57-68);
+ * w: (12,6,3,3), b: (12); writes h_out and (optionally) c_out. */
+int bin_convlstm_fwd(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
+                     float* h_out, float* c_out, int B, int H, int W, bin_stream_t s);
+
+/* ---- one backbone (RDN_residual_interp_{2,2_1,4_1}_input.forward, RDN.py:210-334) ---------- */
+#define BIN_BACKBONE_NCONV 66 /* SFENet1, SFENet2, 12 x (4 conv + LFF), GFF.0, GFF.1, UPNet.0, UPNet.2 */
+size_t bin_backbone_packed_bytes(int nframes);
+/* w[i], b[i]: device fp32 parameters in nn.Module registration order (see bin_b200/rdn.py). */
+int bin_backbone_pack(int nframes, const float* const* w_host, const float* const* b_host, void* blob,
+                      bin_stream_t s);
+size_t bin_backbone_workspace_bytes(int nframes, int Btot, int H, int W);
+int bin_backbone_fwd(int nframes, const void* blob, const bin_frames_t* fr, int H, int W, void* workspace,
+                     size_t workspace_bytes, bin_stream_t s);
+/* Unit-test entry: one RDB (RDN.py:149-165) on fp32 NCHW (B,96,h,w), using RDB `index` of the blob. */
+int bin_rdb_fwd(const void* blob, int nframes, int index, const float* x, float* y, int B, int h, int w,
+                void* workspace, size_t workspace_bytes, bin_stream_t s);
+
+/* ---- whole 6-frame window (RDN_residual_interp_5_input_ConvLSTM_L.forward, RDN.py:422-465) */
+typedef struct {
+  const void* blob[4];      /* packed model1_1, model2_1, model3_1, model4_1 */
+  const float* lstm_w[6];   /* clstm_{4',6',8',5'',7'',6'''}.Gates.weight (12,6,3,3) */
+  const float* lstm_b[6];
+} bin_net_t;
+size_t bin_window_workspace_bytes(int B, int H, int W);
+/* frames[6], outs[14]: (B,3,H,W) fp32 NCHW device tensors.  Executes the 17 unique backbone
+ * calls of the reference's 20 (the 3 repeated stage-1 calls are bit-identical) and the 6 live
+ * ConvLSTM calls of its 12. */
+int bin_window_fwd(const bin_net_t* net, const float* const* frames_host, float* const* outs_host, int B, int H,
+                   int W, void* workspace, size_t workspace_bytes, bin_stream_t s);
+/* BASELINE config 2a/3a: stages 1-3 on 4 frames -> 6 outputs [I2',I4',I6',I3',I5',I4'']. */
+int bin_pyramid3_fwd(const bin_net_t* net, const float* const* frames_host, float* const* outs_host, int B, int H,
+                     int W, void* workspace, size_t workspace_bytes, bin_stream_t s);
+
+/* ---- measurement helpers ---------------------------------------------------------------- */
+/* Issue `iters` back-to-back tcgen05.mma (M=128, N=n, K=16, fp16) from one CTA per SM and
+ * return cycles per MMA in *cycles_host (host pointer; synchronises). mode 0: A/B K-major
+ * no-swizzle. */
+int bin_microbench_mma(int n, int iters, int mode, float* cycles_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIN_B200_H_ */

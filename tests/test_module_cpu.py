@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: schema, strict load, loud failure
+without CUDA, and that the C-ABI library exports every symbol the header declares."""
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import bin_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def net():
+    from bin_b200 import rdn
+    torch.manual_seed(0)
+    return rdn.bin_stage4_lstm()
+
+
+def test_state_dict_schema_matches_reference(net):
+    sd_ref = O.synth_state_dict(0)            # key order + shapes were asserted against the reference in make_golden.py
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(sd_ref.keys())
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(sd_ref[k].shape), k
+    assert len(sd) == 1332
+    uniq = list(net.parameters())
+    assert len(uniq) == 540 and sum(p.numel() for p in uniq) == 11_441_668
+
+
+def test_strict_load_and_aliasing(net):
+    sd_ref = O.synth_state_dict(3)
+    res = net.load_state_dict(sd_ref, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    m = net.model
+    assert m.model1_2 is m.model1_1 and m.model1_4 is m.model1_1 and m.model2_3 is m.model2_1 and m.model3_2 is m.model3_1
+    assert torch.equal(m.model1_3.SFENet1.weight, sd_ref["model.model1_1.SFENet1.weight"])
+
+
+def test_prefix_stripping_like_base_model(net):
+    """base_model.load_network strips 'module.' / 'InterpNet.' prefixes then loads strictly (base_model.py:89-103)."""
+    sd_ref = O.synth_state_dict(1)
+    wrapped = {"module." + k: v for k, v in sd_ref.items()}
+    clean = {k[7:] if k.startswith("module.") else k: v for k, v in wrapped.items()}
+    net.load_state_dict(clean, strict=True)
+
+
+def test_cpu_forward_fails_loudly(net):
+    from bin_b200 import BinB200Error
+    fr = O.synth_frames(6, 1, 16, 16)
+    with torch.no_grad(), pytest.raises(BinB200Error):
+        net(*fr)
+
+
+def test_grad_path_fails_loudly(net):
+    from bin_b200 import BinB200Error
+    fr = O.synth_frames(6, 1, 16, 16)
+    with pytest.raises(BinB200Error):
+        net(*fr)
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from bin_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "bin_b200.h")).read()
+    declared = set(re.findall(r"\b(bin_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"bin_b200"}
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/bin_b200.h but not exported"
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    assert _lib.lib().bin_abi_version() == 1
+
+
+def test_workspace_queries_are_pure():
+    from bin_b200 import _lib
+    L = _lib.lib()
+    assert L.bin_backbone_packed_bytes(2) > 5_000_000 and L.bin_backbone_packed_bytes(4) == 0
+    a = L.bin_window_workspace_bytes(1, 64, 64)
+    assert 0 < a < L.bin_window_workspace_bytes(1, 128, 128)
