@@ -1,0 +1,23 @@
+"""Run N 720p windows (for ncu / timing). usage: run_window.py [n_windows] [H W]"""
+import os
+import sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bin_b200 import rdn  # noqa: E402
+from oracle import bin_oracle as O  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+H, W = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (720, 1280)
+net = rdn.bin_stage4_lstm()
+net.load_state_dict(O.synth_state_dict(0), strict=True)
+net = net.cuda().eval()
+fr = [f.cuda() for f in O.synth_frames(6, 1, H, W, seed=1234, smooth=True)]
+with torch.no_grad():
+    for i in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        outs = net(*fr)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"window {i}: {e0.elapsed_time(e1):.3f} ms", flush=True)
