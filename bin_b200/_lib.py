@@ -29,6 +29,7 @@ class ConvArgs(C.Structure):
                 ("in1", Act), ("in1_plane0", C.c_int), ("in1_planes", C.c_int),
                 ("w_packed", C.c_void_p), ("bias", C.c_void_p),
                 ("ksize", C.c_int), ("cout_pad", C.c_int), ("relu", C.c_int), ("epilogue", C.c_int), ("variant", C.c_int),
+                ("b_begin", C.c_int), ("b_count", C.c_int), ("y_begin", C.c_int), ("y_count", C.c_int),
                 ("out", Act), ("out_plane0", C.c_int),
                 ("res", Act), ("res_plane0", C.c_int),
                 ("fr", Frames)]

@@ -1,6 +1,7 @@
 // bin_b200 -- extern "C" entry points (include/bin_b200.h) and the host-side orchestration of
 // one backbone / one 6-frame window.  Host code only: every arithmetic step is a kernel in
 // conv_igemm.cu / aux_kernels.cu.
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -116,25 +117,101 @@ static bin_conv_args_t conv_args(const void* blob, const ConvSpec& c) {
   return a;
 }
 
+// ------------------------------------------------------------------ L2 band plan for the RDB section
+// An RDB run layer-by-layer over the whole (batched) image moves 2 240 B/position through HBM
+// (each conv re-reads the growing concat); measured, that makes the RDB convs HBM-bound at ~50 % of
+// the tensor peak.  Walking the RDB band by band -- all 5 layers for one band before the next --
+// keeps x (192 B/px) + growth scratch (256 B/px) + x' (192 B/px) of the band inside the 126 MB L2,
+// so only x in / x' out (384 B/position) touch HBM.  Bands overlap by the 3-row receptive field of
+// the chained 3x3 convs (rows are recomputed, values identical).  Boundaries sit at rows 8k-3 so
+// every layer of a band has the same number of 8-row tile rows, and k is chosen to minimise the
+// number of 148-CTA waves.
+struct Band { int b0, nb, y0, y1; };   // batch items [b0,b0+nb), LFF output rows [y0,y1)
+constexpr size_t kBandBytesPerPx = 640;
+static size_t band_budget() {            // BIN_B200_BAND_BUDGET_KB overrides (tests force many bands)
+  const char* e = getenv("BIN_B200_BAND_BUDGET_KB");
+  if (e && *e) return (size_t)atoll(e) << 10;
+  // Measured on B200 (720p, 5 batched calls): with 10 bands the 10x launch count costs more
+  // (prologue + drain per launch, ~4 us each) than the L2 residency saves: 41.5 ms vs 31.8 ms per
+  // window.  Default = one band (off); the walker stays for the fused-RDB work of the next round.
+  return ~(size_t)0 >> 1;
+}
+
+static std::vector<Band> plan_bands(int Btot, int h, int w) {
+  std::vector<Band> out;
+  const size_t px_max = band_budget() / kBandBytesPerPx;
+  const size_t img = (size_t)h * w;
+  if (img <= px_max) {                       // small images: several batch items per band, full rows
+    int per = (int)(px_max / img);
+    if (per < 1) per = 1;
+    for (int b = 0; b < Btot; b += per) out.push_back({b, (b + per <= Btot) ? per : Btot - b, 0, h});
+    return out;
+  }
+  const int tx = (w + 29) / 30;
+  const int T = (h + 7) / 8;                 // boundaries allowed at rows 8k-3, k = 1..T-1
+  const int maxrows = (int)(px_max / w);
+  auto waves = [&](int rows) { int t = ((rows + 7) / 8) * tx; return (t + 147) / 148; };
+  // dp[k] = min waves to cover rows [0, 8k-3) with bands ending at k; last band ends at h.
+  const int INF = 1 << 30;
+  std::vector<int> dp(T + 1, INF), prev(T + 1, -1);
+  dp[0] = 0;
+  int best = INF, best_k = -1;
+  for (int k = 0; k < T; ++k) {
+    if (dp[k] == INF) continue;
+    const int start = k == 0 ? 0 : 8 * k - 3;
+    for (int k2 = k + 1; k2 < T; ++k2) {     // middle band [start, 8*k2-3)
+      const int end = 8 * k2 - 3;
+      if (end <= start || end >= h) continue;
+      if (end - start > maxrows) break;
+      const int lo = start - 3 < 0 ? 0 : start - 3, hi = end + 3 > h ? h : end + 3;
+      const int c = dp[k] + waves(hi - lo);
+      if (c < dp[k2] || (c == dp[k2] && prev[k2] < k)) { dp[k2] = c; prev[k2] = k; }
+    }
+    if (h - start <= maxrows) {               // close with the last band [start, h)
+      const int lo = start - 3 < 0 ? 0 : start - 3;
+      const int c = dp[k] + waves(h - lo);
+      if (c < best) { best = c; best_k = k; }
+    }
+  }
+  std::vector<int> cuts;
+  for (int k = best_k; k > 0; k = prev[k]) cuts.push_back(8 * k - 3);
+  std::vector<int> edges = {0};
+  for (auto it = cuts.rbegin(); it != cuts.rend(); ++it) edges.push_back(*it);
+  edges.push_back(h);
+  if (best_k < 0) edges = {0, h};
+  for (int b = 0; b < Btot; ++b)
+    for (size_t i = 0; i + 1 < edges.size(); ++i) out.push_back({b, 1, edges[i], edges[i + 1]});
+  return out;
+}
+
 // One RDB: 4 x (conv3x3+ReLU -> growth planes) + LFF 1x1 + residual (RDN.py:149-165).
 static int run_rdb(const void* blob, const BackboneLayout& L, int i, const bin_act_t& xin, int x_plane0,
-                   const bin_act_t& g, const bin_act_t& out, int out_plane0, cudaStream_t s) {
+                   const bin_act_t& g, const bin_act_t& out, int out_plane0, const std::vector<Band>& bands,
+                   cudaStream_t s) {
   const int base = 2 + i * (kCgrow + 1);
-  for (int c = 0; c < kCgrow; ++c) {
-    bin_conv_args_t a = conv_args(blob, L.conv[base + c]);
+  const int h = xin.H;
+  for (const Band& bd : bands) {
+    for (int c = 0; c < kCgrow; ++c) {
+      bin_conv_args_t a = conv_args(blob, L.conv[base + c]);
+      a.in0 = xin; a.in0_plane0 = x_plane0; a.in0_planes = 12;
+      a.in1 = g; a.in1_plane0 = 0; a.in1_planes = 4 * c;
+      a.relu = 1; a.epilogue = BIN_EPI_P8;
+      a.out = g; a.out_plane0 = 4 * c;
+      const int ext = kCgrow - 1 - c;             // rows still needed by the convs downstream in this band
+      const int lo = bd.y0 - ext < 0 ? 0 : bd.y0 - ext, hi = bd.y1 + ext > h ? h : bd.y1 + ext;
+      a.b_begin = bd.b0; a.b_count = bd.nb; a.y_begin = lo; a.y_count = hi - lo;
+      BIN_TRY(launch_conv(a, s));
+    }
+    bin_conv_args_t a = conv_args(blob, L.conv[base + kCgrow]);
     a.in0 = xin; a.in0_plane0 = x_plane0; a.in0_planes = 12;
-    a.in1 = g; a.in1_plane0 = 0; a.in1_planes = 4 * c;
-    a.relu = 1; a.epilogue = BIN_EPI_P8;
-    a.out = g; a.out_plane0 = 4 * c;
+    a.in1 = g; a.in1_plane0 = 0; a.in1_planes = 16;
+    a.epilogue = BIN_EPI_P8;
+    a.out = out; a.out_plane0 = out_plane0;
+    a.res = xin; a.res_plane0 = x_plane0;
+    a.b_begin = bd.b0; a.b_count = bd.nb; a.y_begin = bd.y0; a.y_count = bd.y1 - bd.y0;
     BIN_TRY(launch_conv(a, s));
   }
-  bin_conv_args_t a = conv_args(blob, L.conv[base + kCgrow]);
-  a.in0 = xin; a.in0_plane0 = x_plane0; a.in0_planes = 12;
-  a.in1 = g; a.in1_plane0 = 0; a.in1_planes = 16;
-  a.epilogue = BIN_EPI_P8;
-  a.out = out; a.out_plane0 = out_plane0;
-  a.res = xin; a.res_plane0 = x_plane0;
-  return launch_conv(a, s);
+  return BIN_OK;
 }
 
 static int run_backbone(int nframes, const void* blob, const bin_frames_t& fr, int H, int W, void* workspace,
@@ -159,9 +236,10 @@ static int run_backbone(int nframes, const void* blob, const bin_frames_t& fr, i
     a.in0 = ws.f1; a.in0_planes = 12; a.epilogue = BIN_EPI_P8; a.out = ws.f2;
     BIN_TRY(launch_conv(a, s));
   }
+  const std::vector<Band> bands = plan_bands(Btot, H / 2, W / 2);
   for (int i = 0; i < kD; ++i) {                                                 // RDN.py:215-217
-    if (i == 0) BIN_TRY(run_rdb(blob, L, i, ws.f2, 0, ws.g, ws.cat, 0, s));
-    else BIN_TRY(run_rdb(blob, L, i, ws.cat, 12 * (i - 1), ws.g, ws.cat, 12 * i, s));
+    if (i == 0) BIN_TRY(run_rdb(blob, L, i, ws.f2, 0, ws.g, ws.cat, 0, bands, s));
+    else BIN_TRY(run_rdb(blob, L, i, ws.cat, 12 * (i - 1), ws.g, ws.cat, 12 * i, bands, s));
   }
   {
     bin_conv_args_t a = conv_args(blob, L.conv[62]);                             // GFF.0 on the 1152-ch concat (RDN.py:218)
@@ -298,7 +376,7 @@ int bin_rdb_fwd(const void* blob, int nframes, int index, const float* x, float*
   bin_act_t xin = carve(12), g = carve(16), out = carve(12);
   if (off > workspace_bytes) return fail(BIN_ERR_WORKSPACE, "rdb_fwd: workspace too small");
   BIN_TRY(launch_nchw_to_p8(x, kG0, xin, 0, (cudaStream_t)s));
-  BIN_TRY(run_rdb(blob, L, index, xin, 0, g, out, 0, (cudaStream_t)s));
+  BIN_TRY(run_rdb(blob, L, index, xin, 0, g, out, 0, plan_bands(B, h, w), (cudaStream_t)s));
   return launch_p8_to_nchw(out, 0, kG0, y, (cudaStream_t)s);
 }
 

@@ -280,7 +280,7 @@ int launch_pack_weight(const float* w, int cout, int cin, int ks, int cout_pad, 
   const int nt = conv_nt(cout_pad);
   if (cout_pad % nt) return fail(BIN_ERR_ARG, "pack_conv_weight: cout_pad must be <=128 or a multiple of 128");
   const size_t total = (size_t)cout_pad * cin_pad * ks * ks;
-  const int stackx = (ks == 3 && cout_pad == 32 && variant == BIN_CONV_DEFAULT) ? 1 : 0;
+  const int stackx = (ks == 3 && (cout_pad == 32 || cout_pad == 16) && variant == BIN_CONV_DEFAULT) ? 1 : 0;
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, cout, cin, ks, cout_pad, cin_pad, nt, stackx,
                                                           (__half*)packed);
   BIN_CUDA_OK(cudaGetLastError());

@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       const int nh = t % p.nh; t /= p.nh;
       const int txi = t % p.tiles_x; t /= p.tiles_x;
       const int tyi = t % p.tiles_y;
-      const int b = t / p.tiles_y;
-      const int x0 = txi * C::TW - C::PAD, y0 = tyi * kTH - C::PAD;
+      const int b = p.b0 + t / p.tiles_y;
+      const int x0 = txi * C::TW - C::PAD, y0 = p.y0 + tyi * kTH - C::PAD;
       for (int c = 0; c < nchunks; ++c) {
         const bool seg1 = c >= p.nch0;
         const void* tmap = seg1 ? (const void*)&p.tmap1 : (const void*)&p.tmap0;
@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       const int nh = t % p.nh; t /= p.nh;
       const int txi = t % p.tiles_x; t /= p.tiles_x;
       const int tyi = t % p.tiles_y;
-      const int b = t / p.tiles_y;
+      const int b = p.b0 + t / p.tiles_y;
+      const int yend = p.y0 + p.ny;
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
       // residual tile (RDN.py:165, :219) is independent of the accumulators: fetch it first so its
       // global-load latency overlaps the MMAs instead of serialising the epilogue.
@@ -222,13 +223,35 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
 #pragma unroll
           for (int m = 0; m < kMT; ++m) {
             const int L = m * 128 + q * 32 + lane;
-            const int y = tyi * kTH + (L >> 5), x = txi * C::TW + (L & 31);
-            const bool valid = ((L & 31) < C::TW) && (y < p.H) && (x < p.W);
+            const int y = p.y0 + tyi * kTH + (L >> 5), x = txi * C::TW + (L & 31);
+            const bool valid = ((L & 31) < C::TW) && (y < yend) && (x < p.W);
 #pragma unroll
             for (int k = 0; k < NT / 8; ++k) {
               const size_t off = ((((size_t)b * p.res_planes + p.res_plane0 + (nh * NT) / 8 + k) * p.H + y) * p.W + x) * 8;
               rbuf[m * (NT / 8) + k] = valid ? *reinterpret_cast<const uint4*>(p.res + off) : make_uint4(0, 0, 0, 0);
             }
+          }
+        }
+      }
+      float fmean[(EPI == BIN_EPI_FINAL) ? kMT * 3 : 1];
+      if constexpr (EPI == BIN_EPI_FINAL) {
+        // mean of the input frames (RDN.py:221/279/333): independent of the conv -> load it early
+        const int call = b / p.fr.Bc, bb = b % p.fr.Bc;
+        const size_t hw = (size_t)p.H * p.W;
+#pragma unroll
+        for (int m = 0; m < kMT; ++m) {
+          const int L = m * 128 + q * 32 + lane;
+          const int y = p.y0 + tyi * kTH + (L >> 5), x = txi * C::TW + (L & 31);
+          const bool valid = ((L & 31) < C::TW) && (y < yend) && (x < p.W);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float acc = 0.f;
+            if (valid) {
+              const size_t off = ((size_t)bb * 3 + c) * hw + (size_t)y * p.W + x;
+              acc = p.fr.frame[call][0][off];
+              for (int fi = 1; fi < p.fr.nframes; ++fi) acc += p.fr.frame[call][fi][off];
+            }
+            fmean[m * 3 + c] = acc / (float)p.fr.nframes;
           }
         }
       }
@@ -238,8 +261,8 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       for (int m = 0; m < kMT; ++m) {
         const int L = m * 128 + q * 32 + lane;
         const int ty = L >> 5, tx = L & 31;
-        const int y = tyi * kTH + ty, x = txi * C::TW + tx;
-        const bool valid = (tx < C::TW) && (y < p.H) && (x < p.W);
+        const int y = p.y0 + tyi * kTH + ty, x = txi * C::TW + tx;
+        const bool valid = (tx < C::TW) && (y < yend) && (x < p.W);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + m * C::NMMA;
         if constexpr (EPI == BIN_EPI_P8) {
 #pragma unroll
@@ -327,19 +350,33 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
             }
           }
         } else {  // BIN_EPI_FINAL: fp32 NCHW = conv + bias + mean(frames)
-          uint32_t v[16];
-          tmem_ld16(taddr, v);
-          tmem_ld_wait();
+          float cv[3];
+          if constexpr (SX) {
+            uint32_t v0[16], v1[16], v2[16];
+            tmem_ld16(taddr, v0);
+            tmem_ld16(taddr + NT, v1);
+            tmem_ld16(taddr + 2 * NT, v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[c]), 1);
+              const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c]), 2);
+              cv[c] = (__uint_as_float(v0[c]) + b1) + b2;
+            }
+          } else {
+            uint32_t v[16];
+            tmem_ld16(taddr, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 3; ++c) cv[c] = __uint_as_float(v[c]);
+          }
           if (valid) {
             const int call = b / p.fr.Bc, bb = b % p.fr.Bc;
             const size_t hw = (size_t)p.H * p.W;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               const size_t off = ((size_t)bb * 3 + c) * hw + (size_t)y * p.W + x;
-              float acc = p.fr.frame[call][0][off];
-              for (int fi = 1; fi < p.fr.nframes; ++fi) acc += p.fr.frame[call][fi][off];
-              const float mean = acc / (float)p.fr.nframes;
-              p.fr.out[call][off] = (__uint_as_float(v[c]) + sbias[c]) + mean;
+              p.fr.out[call][off] = (cv[c] + sbias[c]) + fmean[m * 3 + c];
             }
           }
         }
@@ -419,10 +456,15 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
   p.w = reinterpret_cast<const __half*>(a.w_packed);
   p.bias = a.bias;
   p.H = H; p.W = W; p.Btot = B;
+  p.b0 = a.b_begin; p.y0 = a.y_begin;
+  const int nb = a.b_count > 0 ? a.b_count : B - a.b_begin;
+  p.ny = a.y_count > 0 ? a.y_count : H - a.y_begin;
+  if (p.b0 < 0 || p.y0 < 0 || nb < 1 || p.ny < 1 || p.b0 + nb > B || p.y0 + p.ny > H)
+    return fail(BIN_ERR_ARG, "conv: batch/row sub-range outside the tensor");
   p.tiles_x = (W + C::TW - 1) / C::TW;
-  p.tiles_y = (H + kTH - 1) / kTH;
+  p.tiles_y = (p.ny + kTH - 1) / kTH;
   p.nh = a.cout_pad / NT;
-  p.ntiles = B * p.tiles_x * p.tiles_y * p.nh;
+  p.ntiles = nb * p.tiles_x * p.tiles_y * p.nh;
   p.relu = a.relu;
   const int nchunks = p.nch0 + p.nch1;
   // keep the whole weight set resident in smem when it leaves room for >= 3 activation stages
@@ -477,7 +519,8 @@ int launch_conv(const bin_conv_args_t& a, cudaStream_t s) {
     if (a.fr.ncalls < 1 || a.fr.ncalls > BIN_MAX_CALLS || a.fr.nframes < 1 || a.fr.nframes > BIN_MAX_FRAMES ||
         a.fr.ncalls * a.fr.Bc != a.in0.B)
       return fail(BIN_ERR_ARG, "frame table does not match the batch");
-    if (a.ksize == 3 && a.cout_pad == 16) return launch_inst<16, 3, BIN_EPI_FINAL, false>(a, s);
+    if (a.ksize == 3 && a.cout_pad == 16 && a.variant == 0) return launch_inst<16, 3, BIN_EPI_FINAL, true>(a, s);
+    if (a.ksize == 3 && a.cout_pad == 16 && a.variant == 1) return launch_inst<16, 3, BIN_EPI_FINAL, false>(a, s);
   }
   return fail(BIN_ERR_UNSUPPORTED, "no kernel instantiation for this conv (ksize/cout_pad/epilogue)");
 }

@@ -42,6 +42,7 @@ struct alignas(64) ConvParams {
   const __half* w;
   const float* bias;
   int H, W, Btot;                      // conv resolution
+  int b0, y0, ny;                      // batch / row sub-range processed by this launch
   int tiles_x, tiles_y, ntiles, nh;    // nh = cout_pad / NT
   int relu, resident, nstages;
   __half* out; int out_planes, out_plane0;

@@ -90,6 +90,10 @@ typedef struct {
   int relu;      /* RDN.py:142 */
   int epilogue;  /* BIN_EPI_* */
   int variant;   /* BIN_CONV_*; must match the variant the weights were packed with */
+  /* optional sub-range of the output: batch items [b_begin, b_begin+b_count) and rows
+   * [y_begin, y_begin+y_count); counts of 0 mean "to the end".  Used to walk an RDB band by band
+   * so that its intermediate tensors stay L2-resident. */
+  int b_begin, b_count, y_begin, y_count;
   /* BIN_EPI_P8: out planes [out_plane0, +cout_pad/8), optional residual (RDN.py:165, :219) */
   bin_act_t out; int out_plane0;
   bin_act_t res; int res_plane0; /* res.ptr = NULL -> none */

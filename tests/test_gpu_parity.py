@@ -113,6 +113,17 @@ def test_window_vs_oracle_and_psnr(net, sd, B, H, W):
         assert abs(p_ref - p_got) <= 0.01, (k, p_ref, p_got)
 
 
+def test_window_many_l2_bands(net, sd, monkeypatch):
+    """Force the RDB band walker (L2 blocking) to cut a small image into several overlapping bands."""
+    monkeypatch.setenv("BIN_B200_BAND_BUDGET_KB", "700")         # ~17 low-res rows of 64 px per band
+    fr = O.synth_frames(6, 1, 112, 128, seed=21, smooth=True)
+    ref = O.window_forward(fr, sd)
+    with torch.no_grad():
+        outs = net(*[f.cuda() for f in fr])
+    for k in range(14):
+        assert (outs[k].cpu() - ref[k]).abs().max().item() <= TOL_FP16, k
+
+
 def test_pyramid3_config2a(net, sd):
     fr = O.synth_frames(4, 1, 40, 72, seed=5)
     ref = O.pyramid3_4frames(fr, sd)

@@ -21,3 +21,21 @@ with torch.no_grad():
         e1.record()
         torch.cuda.synchronize()
         print(f"window {i}: {e0.elapsed_time(e1):.3f} ms", flush=True)
+if "--graph" in sys.argv:
+    g = torch.cuda.CUDAGraph()
+    with torch.no_grad():
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            net(*fr)
+        torch.cuda.current_stream().wait_stream(s)
+        with torch.cuda.graph(g):
+            gouts = net(*fr)
+    for i in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"graph window {i}: {e0.elapsed_time(e1):.3f} ms", flush=True)
+    print("graph outputs equal eager:", all(torch.equal(a, b) for a, b in zip(gouts, outs)))
