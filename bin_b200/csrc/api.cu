@@ -142,7 +142,8 @@ static std::vector<Band> plan_bands(int Btot, int h, int w) {
   const size_t px_max = band_budget() / kBandBytesPerPx;
   const size_t img = (size_t)h * w;
   if (img <= px_max) {                       // small images: several batch items per band, full rows
-    int per = (int)(px_max / img);
+    const size_t per_sz = px_max / img;
+    int per = per_sz >= (size_t)Btot ? Btot : (int)per_sz;
     if (per < 1) per = 1;
     for (int b = 0; b < Btot; b += per) out.push_back({b, (b + per <= Btot) ? per : Btot - b, 0, h});
     return out;
@@ -431,6 +432,14 @@ int bin_pyramid3_fwd(const bin_net_t* net, const float* const* F, float* const* 
   BIN_TRY(run_stage(net, 1, 3, {{{o[0], o[0], o[1]}, o[3]}, {{o[1], o[1], o[2]}, o[4]}}, B, H, W, workspace,
                     workspace_bytes, s));
   return run_stage(net, 2, 5, {{{o[3], F[1], o[3], o[4], F[2]}, o[5]}}, B, H, W, workspace, workspace_bytes, s);
+}
+
+int bin_debug_timeline(long long* host, int n) {
+  if (!g_dbg) return fail(BIN_ERR_ARG, "no timeline recorded (set BIN_B200_DEBUG=8)");
+  if (n > 3 * 4096) n = 3 * 4096;
+  BIN_CUDA_OK(cudaDeviceSynchronize());
+  BIN_CUDA_OK(cudaMemcpy(host, g_dbg, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
+  return BIN_OK;
 }
 
 int bin_microbench_mma(int n, int iters, int mode, float* cycles_host) { return run_mma_bench(n, iters, mode, cycles_host); }

@@ -238,6 +238,71 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(int n, int iters, int
   }
 }
 
+// Replays the exact descriptor sequence of the x-stacked RDB conv0 MMA loop (3 resident weight
+// chunks, 3 activation stages, 2 accumulators x 3 ky taps x 2 k-steps, N=96) with no TMA and no
+// epilogue.  vary bit0: A addresses as in the kernel (else one fixed tile); bit1: B addresses as in the
+// kernel (else one fixed slab); bit2: fill smem with non-zero data.
+__global__ void __launch_bounds__(128, 1) mma_pattern_kernel(int tiles, int vary, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = (vary & 4) ? 0x3c003800u + (i * 2654435761u & 0x03ff03ffu) : 0u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (threadIdx.x < 32) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base_s;
+  if (threadIdx.x < 32) {
+    constexpr int NM = 96, A_PLANE = 10 * 32 * 16, W_TAP = 4 * NM * 16, W_CHUNK = 3 * W_TAP, STAGE = 4 * A_PLANE;
+    constexpr uint32_t idesc = umma_idesc_f16(128, NM);
+    constexpr uint32_t HI = (128u >> 4) | (1u << 14);
+    const uint32_t wbase = smem_u32(smem), sbase = smem_u32(smem + 3 * W_CHUNK);
+    const long long t0 = clock64();
+    for (int t = 0; t < tiles; ++t) {
+      for (int c = 0; c < 3; ++c) {
+        const uint32_t a_lo = (((sbase + ((vary & 1) ? c * STAGE : 0)) >> 4) & 0x3FFFu) | ((uint32_t)(A_PLANE >> 4) << 16);
+        const uint32_t b_lo = (((wbase + ((vary & 2) ? c * W_CHUNK : 0)) >> 4) & 0x3FFFu) | ((uint32_t)(NM * 16 >> 4) << 16);
+        if (elect_one()) {
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+#pragma unroll
+            for (int tp = 0; tp < 3; ++tp) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint32_t ao = (vary & 1) ? (uint32_t)(m * 128 + tp * 32) + j * 2 * (A_PLANE >> 4) : 0u;
+                const uint32_t bo = (vary & 2) ? (uint32_t)(tp * W_TAP + j * 2 * NM * 16) / 16 : 0u;
+                umma_f16_ss(tb + (t & 1) * 192 + m * NM, ((uint64_t)HI << 32) | (a_lo + ao),
+                            ((uint64_t)HI << 32) | (b_lo + bo), idesc, 1u);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    tmem_dealloc(tb, 512);
+  }
+}
+
 // ------------------------------------------------------------------ launch wrappers
 static inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
@@ -304,8 +369,14 @@ int run_mma_bench(int n, int iters, int mode, float* cycles_host) {
   long long* d = nullptr;
   const int grid = 148;
   BIN_CUDA_OK(cudaMalloc(&d, grid * sizeof(long long)));
+  if (mode & 0x1000) {                       // conv-pattern replay: n = ignored, iters = tiles
+    BIN_CUDA_OK(cudaFuncSetAttribute(mma_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    mma_pattern_kernel<<<grid, 128, 160 * 1024>>>(iters, mode & 7, d);
+    iters *= 36;
+  } else {
   BIN_CUDA_OK(cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   mma_bench_kernel<<<grid, 128, 96 * 1024>>>(n, iters, mode, d);
+  }
   BIN_CUDA_OK(cudaGetLastError());
   BIN_CUDA_OK(cudaDeviceSynchronize());
   long long h[148];

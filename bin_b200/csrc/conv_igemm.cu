@@ -22,6 +22,7 @@
 //                   double-buffered against the next tile's MMAs through tmem_full/empty.
 // Weight sets that fit (RDB convs, LFF, SFENet2, GFF.1, UPNet.2) stay resident in shared memory.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -65,6 +66,7 @@ struct Ctrl {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
+  volatile uint32_t issued;   // number of pipeline stages whose MMAs have been issued (MMA warp hand-off)
 };
 static_assert(sizeof(Ctrl) <= 1024, "ctrl block");
 
@@ -77,8 +79,30 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
   return __half22float2(h);
 }
 
+// perf-debug timeline (BIN_B200_DEBUG=8): block 0 records clock64 at role milestones.
+// layout: dbg[role*4096 + iter*4 + k], role 0 = producer A, 1 = MMA warp A, 2 = epilogue (warp 4).
+__device__ __forceinline__ void dbg_rec(const ConvParams& p, int role, uint32_t iter, int k) {
+  if ((p.debug & 8) && blockIdx.x == 0 && iter < 1024) p.dbg[role * 4096 + iter * 4 + k] = clock64();
+}
+
+constexpr int kThreads = 384;   // 12 warps, see the role table below
+
+// Warp roles (384 threads, 1 CTA/SM, persistent over tiles).  Measured on B200: one mbarrier poll
+// costs 200-350 cycles even when the phase is already complete, so a single MMA warp that polls
+// once per 12-MMA stage leaves the tensor pipe idle ~50 % of the time.  Hence every role that sits
+// on a latency chain is doubled and the two copies work on alternating items:
+//   warp 0 lane 0 : TMA producer A                              warp 2 : TMEM alloc, then TMA producer B
+//   warp 1        : MMA issuer  A  (accumulator 0)              warp 3 : MMA issuer B (accumulator 1)
+//   warps 4..11   : epilogue, warp w handles TMEM lane quarter w%4 of accumulator tile (w-4)/4
+// One ring of S (even) smem stages; stage i is filled by producer i%2 and its MMAs are issued by MMA
+// warp i%2.  Both MMA warps observe EVERY full barrier in order (a waiter may never fall two phases
+// behind a parity-tracked mbarrier) and hand the tensor pipe to each other through a shared-memory
+// counter, so one warp's barrier poll / descriptor setup overlaps the other's issue phase.  The two
+// TMEM accumulator buffers alternate per tile and are released by the epilogue (tmem_full counts
+// one tcgen05.commit per MMA warp).
+// A pipeline stage holds up to p.cps "units" (unit = one 32-channel chunk, or one (chunk, ky) for 5x5).
 template <int NT, int KS, int EPI, bool SX>
-__global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using C = ConvCfg<NT, KS, SX>;
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
@@ -86,9 +110,13 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int S = p.nstages;
+  const uint32_t S = p.nstages;
   const int nchunks = p.nch0 + p.nch1;
-  const int stage_bytes = C::A_BYTES + (p.resident ? 0 : C::W_STAGE);
+  const int nunits = nchunks * C::NSUB;
+  const int cps = p.cps;
+  const int spt = (nunits + cps - 1) / cps;                   // stages per tile
+  const int unit_bytes = C::A_BYTES + (p.resident ? 0 : C::W_STAGE);
+  const int stage_bytes = cps * unit_bytes;
   uint8_t* res_w = smem + kCtrlBytes;
   uint8_t* stage0 = res_w + (p.resident ? nchunks * C::W_CHUNK : 0);
 
@@ -102,9 +130,10 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
     }
     for (int i = 0; i < kMaxResidentChunks; ++i) mbar_init(&ctrl->wfull[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&ctrl->tmem_full[i], 1);
-      mbar_init(&ctrl->tmem_empty[i], 128);
+      mbar_init(&ctrl->tmem_full[i], 2);
+      mbar_init(&ctrl->tmem_empty[i], 256);
     }
+    ctrl->issued = 0;
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < NT * p.nh; i += blockDim.x) sbias[i] = p.bias[i];
@@ -117,16 +146,17 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
 
-  if (warp == 0 && lane == 0) {
-    // ========================================================== TMA producer
-    if (p.resident) {
+  if ((warp == 0 || warp == 2) && lane == 0) {
+    // ========================================================== TMA producers (stage i -> producer i%2)
+    const uint32_t Y = warp >> 1;
+    if (p.resident && Y == 0) {
       for (int c = 0; c < nchunks; ++c) {
         mbar_expect_tx(&ctrl->wfull[c], C::W_CHUNK);
         bulk_load_1d(res_w + c * C::W_CHUNK, reinterpret_cast<const uint8_t*>(p.w) + (size_t)c * C::W_CHUNK,
                      C::W_CHUNK, &ctrl->wfull[c]);
       }
     }
-    uint32_t it = 0;
+    uint32_t it = 0, s = 0, ph = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int t = tile;
       const int nh = t % p.nh; t /= p.nh;
@@ -134,78 +164,104 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       const int tyi = t % p.tiles_y;
       const int b = p.b0 + t / p.tiles_y;
       const int x0 = txi * C::TW - C::PAD, y0 = p.y0 + tyi * kTH - C::PAD;
-      for (int c = 0; c < nchunks; ++c) {
-        const bool seg1 = c >= p.nch0;
-        const void* tmap = seg1 ? (const void*)&p.tmap1 : (const void*)&p.tmap0;
-        const int plane = seg1 ? p.plane0_1 + (c - p.nch0) * kKPL : p.plane0_0 + c * kKPL;
-        for (int sub = 0; sub < C::NSUB; ++sub, ++it) {
-          const uint32_t s = it % S, ph = (it / S) & 1;
+      int unit = 0;
+      for (int j = 0; j < spt; ++j, ++it) {
+        const int nu = (nunits - unit < cps) ? nunits - unit : cps;
+        if ((it & 1u) == Y) {
+          if (Y == 0) dbg_rec(p, 0, it >> 1, 0);
           mbar_wait(&ctrl->empty[s], ph ^ 1);
-          uint8_t* a_dst = stage0 + (size_t)s * stage_bytes;
-          mbar_expect_tx(&ctrl->full[s], stage_bytes);
-          tma_load_4d(a_dst, tmap, &ctrl->full[s], x0 * 8, y0 + (C::ROWSPLIT ? sub : 0), plane, b);
-          if (!p.resident) {
-            const size_t woff = ((size_t)(nh * nchunks + c) * C::TAPS_C + (C::ROWSPLIT ? sub * KS : 0)) * C::W_TAP;
-            bulk_load_1d(a_dst + C::A_BYTES, reinterpret_cast<const uint8_t*>(p.w) + woff, C::W_STAGE,
-                         &ctrl->full[s]);
+          if (Y == 0) dbg_rec(p, 0, it >> 1, 1);
+          uint8_t* dst = stage0 + (size_t)s * stage_bytes;
+          mbar_expect_tx(&ctrl->full[s], (uint32_t)(nu * unit_bytes));
+          for (int u = 0; u < nu; ++u) {
+            const int c = (unit + u) / C::NSUB, sub = (unit + u) % C::NSUB;
+            const bool seg1 = c >= p.nch0;
+            const void* tmap = seg1 ? (const void*)&p.tmap1 : (const void*)&p.tmap0;
+            const int plane = seg1 ? p.plane0_1 + (c - p.nch0) * kKPL : p.plane0_0 + c * kKPL;
+            tma_load_4d(dst + (size_t)u * unit_bytes, tmap, &ctrl->full[s], x0 * 8, y0 + (C::ROWSPLIT ? sub : 0), plane, b);
+            if (!p.resident) {
+              const size_t woff = ((size_t)(nh * nchunks + c) * C::TAPS_C + (C::ROWSPLIT ? sub * KS : 0)) * C::W_TAP;
+              bulk_load_1d(dst + (size_t)u * unit_bytes + C::A_BYTES, reinterpret_cast<const uint8_t*>(p.w) + woff,
+                           C::W_STAGE, &ctrl->full[s]);
+            }
           }
         }
+        unit += nu;
+        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ========================================================== MMA issuer (warp converged, one elected lane)
+  } else if (warp == 1 || warp == 3) {
+    // ========================================================== MMA issuers (warp converged, one elected lane)
+    const uint32_t Y = warp >> 1;
     constexpr uint32_t idesc = umma_idesc_f16(128, C::NMMA);
-    constexpr uint32_t A_HI = (128u >> 4) | (1u << 14);            // SBO=128 B, descriptor version 1
+    constexpr uint32_t D_HI = (128u >> 4) | (1u << 14);            // SBO=128 B, descriptor version 1
     constexpr uint32_t A_LBO = ((uint32_t)C::A_PLANE >> 4) << 16;
     constexpr uint32_t B_LBO = ((uint32_t)(C::NMMA * 16) >> 4) << 16;
-    uint32_t it = 0, acc_it = 0;
-    bool first_tile = true;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++acc_it) {
-      const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+    uint32_t it = 0, s = 0, ph = 0, tl = 0, dbg_it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tl) {
+      const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
       mbar_wait(&ctrl->tmem_empty[as], aph ^ 1);
       tc_fence_after();
-      for (int c = 0; c < nchunks; ++c) {
-        if (p.resident && first_tile) mbar_wait(&ctrl->wfull[c], 0);
-        for (int sub = 0; sub < C::NSUB; ++sub, ++it) {
-          const uint32_t s = it % S, ph = (it / S) & 1;
-          mbar_wait(&ctrl->full[s], ph);
+      int unit = 0;
+      for (int j = 0; j < spt; ++j, ++it) {
+        const int nu = (nunits - unit < cps) ? nunits - unit : cps;
+        const bool mine = (it & 1u) == Y;
+        if (mine && Y == 0 && lane == 0) dbg_rec(p, 1, dbg_it, 0);
+        mbar_wait(&ctrl->full[s], ph);                      // both warps observe every phase
+        if (mine) {
+          if (p.resident && tl == 0) {
+            for (int u = 0; u < nu; ++u)
+              if ((unit + u) % C::NSUB == 0) mbar_wait(&ctrl->wfull[(unit + u) / C::NSUB], 0);
+          }
+          while (ctrl->issued < it) { }                     // stage it-1 fully issued by the other warp
+          if (Y == 0 && lane == 0) dbg_rec(p, 1, dbg_it, 1);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(stage0 + (size_t)s * stage_bytes);
-          const uint32_t w_base = p.resident
-                                      ? smem_u32(res_w + c * C::W_CHUNK) + (C::ROWSPLIT ? sub * KS * C::W_TAP : 0)
-                                      : a_base + C::A_BYTES;
-          const uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | A_LBO;
-          const uint32_t b_lo = ((w_base >> 4) & 0x3FFFu) | B_LBO;
-          const uint32_t not_first = (c | sub) != 0 ? 1u : 0u;
-          if (elect_one()) {
+          const uint32_t st_base = smem_u32(stage0 + (size_t)s * stage_bytes);
+          for (int u = 0; u < nu; ++u) {
+            const int c = (unit + u) / C::NSUB, sub = (unit + u) % C::NSUB;
+            const uint32_t a_base = st_base + u * unit_bytes;
+            const uint32_t w_base = p.resident
+                                        ? smem_u32(res_w + c * C::W_CHUNK) + (C::ROWSPLIT ? sub * KS * C::W_TAP : 0)
+                                        : a_base + C::A_BYTES;
+            const uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | A_LBO;
+            const uint32_t b_lo = ((w_base >> 4) & 0x3FFFu) | B_LBO;
+            const uint32_t not_first = (unit + u) != 0 ? 1u : 0u;
+            if (elect_one()) {
 #pragma unroll
-            for (int m = 0; m < kMT; ++m) {
-              const uint32_t d = tmem_base + as * C::ACC_COLS + m * C::NMMA;
+              for (int m = 0; m < kMT; ++m) {
+                const uint32_t d = tmem_base + as * C::ACC_COLS + m * C::NMMA;
 #pragma unroll
-              for (int tp = 0; tp < C::TAPS_S; ++tp) {
-                const int ky = SX ? tp : (C::ROWSPLIT ? 0 : tp / KS);
-                const int kx = SX ? 0 : (C::ROWSPLIT ? tp : tp % KS);
-                const uint32_t a_off = (uint32_t)(m * 128 + ky * kTWH + kx);   // in 16-byte rows
+                for (int tp = 0; tp < C::TAPS_S; ++tp) {
+                  const int ky = SX ? tp : (C::ROWSPLIT ? 0 : tp / KS);
+                  const int kx = SX ? 0 : (C::ROWSPLIT ? tp : tp % KS);
+                  const uint32_t a_off = (uint32_t)(m * 128 + ky * kTWH + kx);   // in 16-byte rows
 #pragma unroll
-                for (int j = 0; j < kKC / 16; ++j) {
-                  const uint64_t ad = ((uint64_t)A_HI << 32) | (a_lo + a_off + j * 2 * (C::A_PLANE >> 4));
-                  const uint64_t bd = ((uint64_t)A_HI << 32) | (b_lo + (tp * C::W_TAP + j * 2 * C::NMMA * 16) / 16);
-                  umma_f16_ss(d, ad, bd, idesc, (tp == 0 && j == 0) ? not_first : 1u);
+                  for (int jj = 0; jj < kKC / 16; ++jj) {
+                    const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + a_off + jj * 2 * (C::A_PLANE >> 4));
+                    const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + (tp * C::W_TAP + jj * 2 * C::NMMA * 16) / 16);
+                    umma_f16_ss(d, ad, bd, idesc, (tp == 0 && jj == 0) ? not_first : 1u);
+                  }
                 }
               }
             }
-            umma_commit(&ctrl->empty[s]);   // frees the smem stage once these MMAs retire
+            __syncwarp();
           }
+          if (elect_one()) umma_commit(&ctrl->empty[s]);   // frees the smem stage once these MMAs retire
           __syncwarp();
+          if (lane == 0) ctrl->issued = it + 1;            // hand the tensor pipe to the other MMA warp
+          if (Y == 0 && lane == 0) dbg_rec(p, 1, dbg_it, 2);
+          ++dbg_it;
         }
+        unit += nu;
+        if (++s == S) { s = 0; ph ^= 1; }
       }
-      if (elect_one()) umma_commit(&ctrl->tmem_full[as]);  // accumulators of this tile complete
+      if (elect_one()) umma_commit(&ctrl->tmem_full[as]);  // this warp's share of the tile's MMAs
       __syncwarp();
-      first_tile = false;
     }
   } else if (warp >= 4) {
     // ========================================================== epilogue
     const int q = warp & 3;
+    const int m = (warp - 4) >> 2;                      // which 128-row accumulator of the tile
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++acc_it) {
       int t = tile;
@@ -215,174 +271,162 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       const int b = p.b0 + t / p.tiles_y;
       const int yend = p.y0 + p.ny;
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-      // residual tile (RDN.py:165, :219) is independent of the accumulators: fetch it first so its
-      // global-load latency overlaps the MMAs instead of serialising the epilogue.
-      uint4 rbuf[(EPI == BIN_EPI_P8 && !SX) ? kMT * (NT / 8) : 1];
+      const int L = m * 128 + q * 32 + lane;
+      const int ty = L >> 5, tx = L & 31;
+      const int y = p.y0 + tyi * kTH + ty, x = txi * C::TW + tx;
+      const bool valid = (tx < C::TW) && (y < yend) && (x < p.W);
+      // operands of the epilogue that do not depend on the accumulators are fetched BEFORE waiting for
+      // them, so their global-load latency overlaps the MMAs: the residual tile (RDN.py:165, :219) ...
+      uint4 rbuf[(EPI == BIN_EPI_P8 && !SX) ? (NT / 8) : 1];
       if constexpr (EPI == BIN_EPI_P8 && !SX) {
         if (p.res != nullptr) {
 #pragma unroll
-          for (int m = 0; m < kMT; ++m) {
-            const int L = m * 128 + q * 32 + lane;
-            const int y = p.y0 + tyi * kTH + (L >> 5), x = txi * C::TW + (L & 31);
-            const bool valid = ((L & 31) < C::TW) && (y < yend) && (x < p.W);
-#pragma unroll
-            for (int k = 0; k < NT / 8; ++k) {
-              const size_t off = ((((size_t)b * p.res_planes + p.res_plane0 + (nh * NT) / 8 + k) * p.H + y) * p.W + x) * 8;
-              rbuf[m * (NT / 8) + k] = valid ? *reinterpret_cast<const uint4*>(p.res + off) : make_uint4(0, 0, 0, 0);
-            }
+          for (int k = 0; k < NT / 8; ++k) {
+            const size_t off = ((((size_t)b * p.res_planes + p.res_plane0 + (nh * NT) / 8 + k) * p.H + y) * p.W + x) * 8;
+            rbuf[k] = valid ? *reinterpret_cast<const uint4*>(p.res + off) : make_uint4(0, 0, 0, 0);
           }
         }
       }
-      float fmean[(EPI == BIN_EPI_FINAL) ? kMT * 3 : 1];
+      // ... and the mean of the input frames (RDN.py:221/279/333)
+      float fmean[(EPI == BIN_EPI_FINAL) ? 3 : 1];
       if constexpr (EPI == BIN_EPI_FINAL) {
-        // mean of the input frames (RDN.py:221/279/333): independent of the conv -> load it early
         const int call = b / p.fr.Bc, bb = b % p.fr.Bc;
         const size_t hw = (size_t)p.H * p.W;
 #pragma unroll
-        for (int m = 0; m < kMT; ++m) {
-          const int L = m * 128 + q * 32 + lane;
-          const int y = p.y0 + tyi * kTH + (L >> 5), x = txi * C::TW + (L & 31);
-          const bool valid = ((L & 31) < C::TW) && (y < yend) && (x < p.W);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float acc = 0.f;
-            if (valid) {
-              const size_t off = ((size_t)bb * 3 + c) * hw + (size_t)y * p.W + x;
-              acc = p.fr.frame[call][0][off];
-              for (int fi = 1; fi < p.fr.nframes; ++fi) acc += p.fr.frame[call][fi][off];
-            }
-            fmean[m * 3 + c] = acc / (float)p.fr.nframes;
+        for (int c = 0; c < 3; ++c) {
+          float acc = 0.f;
+          if (valid) {
+            const size_t off = ((size_t)bb * 3 + c) * hw + (size_t)y * p.W + x;
+            acc = p.fr.frame[call][0][off];
+            for (int fi = 1; fi < p.fr.nframes; ++fi) acc += p.fr.frame[call][fi][off];
           }
+          fmean[c] = acc / (float)p.fr.nframes;
         }
       }
+      if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 0);
       mbar_wait(&ctrl->tmem_full[as], aph);
+      if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 1);
       tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + m * C::NMMA;
+      if constexpr (EPI == BIN_EPI_P8) {
 #pragma unroll
-      for (int m = 0; m < kMT; ++m) {
-        const int L = m * 128 + q * 32 + lane;
-        const int ty = L >> 5, tx = L & 31;
-        const int y = p.y0 + tyi * kTH + ty, x = txi * C::TW + tx;
-        const bool valid = (tx < C::TW) && (y < yend) && (x < p.W);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + m * C::NMMA;
-        if constexpr (EPI == BIN_EPI_P8) {
-#pragma unroll
-          for (int n0 = 0; n0 < NT; n0 += 16) {
-            float f[16];
-            if constexpr (SX) {
-              // out[p] = D[p][kx=0] + D[p+1][kx=1] + D[p+2][kx=2]; p+1, p+2 are lanes +1, +2 of this warp
-              uint32_t v0[16], v1[16], v2[16];
-              tmem_ld16(taddr + n0, v0);
-              tmem_ld16(taddr + NT + n0, v1);
-              tmem_ld16(taddr + 2 * NT + n0, v2);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), 1);
-                const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 2);
-                f[i] = ((__uint_as_float(v0[i]) + b1) + b2) + sbias[n0 + i];
-              }
-            } else {
-              uint32_t v[16];
-              tmem_ld16(taddr + n0, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + sbias[nh * NT + n0 + i];
-            }
-            if (valid) {
-              if (p.relu) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-              }
-              const int cpl = (nh * NT + n0) >> 3;   // channel plane of f[0]
-              if (!SX && p.res != nullptr) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const uint4 r = rbuf[SX ? 0 : m * (NT / 8) + n0 / 8 + h];
-                  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float2 g = unpack_h2(rr[i]);
-                    f[h * 8 + 2 * i] += g.x;
-                    f[h * 8 + 2 * i + 1] += g.y;
-                  }
-                }
-              }
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                uint4 o;
-                o.x = pack_h2(f[h * 8 + 0], f[h * 8 + 1]);
-                o.y = pack_h2(f[h * 8 + 2], f[h * 8 + 3]);
-                o.z = pack_h2(f[h * 8 + 4], f[h * 8 + 5]);
-                o.w = pack_h2(f[h * 8 + 6], f[h * 8 + 7]);
-                const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + cpl + h) * p.H + y) * p.W + x) * 8;
-                *reinterpret_cast<uint4*>(p.out + off) = o;
-              }
-            }
-          }
-        } else if constexpr (EPI == BIN_EPI_PIXSHUF) {
-          // out[c, 2y+i, 2x+j] = conv[4c+2i+j, y, x]   (nn.PixelShuffle(2), RDN.py:206)
-#pragma unroll 1
-          for (int n0 = 0; n0 < NT; n0 += 32) {
-            uint32_t v0[16], v1[16];
-            tmem_ld16(taddr + n0, v0);
-            tmem_ld16(taddr + n0 + 16, v1);
-            tmem_ld_wait();
-            if (valid) {
-              float f[32];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                f[i] = __uint_as_float(v0[i]) + sbias[nh * NT + n0 + i];
-                f[16 + i] = __uint_as_float(v1[i]) + sbias[nh * NT + n0 + 16 + i];
-              }
-              const int opl = (nh * NT + n0) >> 5;   // output plane (8 channels = 32 conv channels)
-              const int H2 = 2 * p.H, W2 = 2 * p.W;
-#pragma unroll
-              for (int ij = 0; ij < 4; ++ij) {
-                uint4 o;
-                o.x = pack_h2(f[0 * 4 + ij], f[1 * 4 + ij]);
-                o.y = pack_h2(f[2 * 4 + ij], f[3 * 4 + ij]);
-                o.z = pack_h2(f[4 * 4 + ij], f[5 * 4 + ij]);
-                o.w = pack_h2(f[6 * 4 + ij], f[7 * 4 + ij]);
-                const int yy = 2 * y + (ij >> 1), xx = 2 * x + (ij & 1);
-                const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + opl) * H2 + yy) * W2 + xx) * 8;
-                *reinterpret_cast<uint4*>(p.out + off) = o;
-              }
-            }
-          }
-        } else {  // BIN_EPI_FINAL: fp32 NCHW = conv + bias + mean(frames)
-          float cv[3];
+        for (int n0 = 0; n0 < NT; n0 += 16) {
+          float f[16];
           if constexpr (SX) {
+            // out[p] = D[p][kx=0] + D[p+1][kx=1] + D[p+2][kx=2]; p+1, p+2 are lanes +1, +2 of this warp
             uint32_t v0[16], v1[16], v2[16];
-            tmem_ld16(taddr, v0);
-            tmem_ld16(taddr + NT, v1);
-            tmem_ld16(taddr + 2 * NT, v2);
+            tmem_ld16(taddr + n0, v0);
+            tmem_ld16(taddr + NT + n0, v1);
+            tmem_ld16(taddr + 2 * NT + n0, v2);
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[c]), 1);
-              const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c]), 2);
-              cv[c] = (__uint_as_float(v0[c]) + b1) + b2;
+            for (int i = 0; i < 16; ++i) {
+              const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), 1);
+              const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 2);
+              f[i] = ((__uint_as_float(v0[i]) + b1) + b2) + sbias[n0 + i];
             }
           } else {
             uint32_t v[16];
-            tmem_ld16(taddr, v);
+            tmem_ld16(taddr + n0, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 3; ++c) cv[c] = __uint_as_float(v[c]);
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + sbias[nh * NT + n0 + i];
           }
           if (valid) {
-            const int call = b / p.fr.Bc, bb = b % p.fr.Bc;
-            const size_t hw = (size_t)p.H * p.W;
+            if (p.relu) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const size_t off = ((size_t)bb * 3 + c) * hw + (size_t)y * p.W + x;
-              p.fr.out[call][off] = (cv[c] + sbias[c]) + fmean[m * 3 + c];
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
             }
+            const int cpl = (nh * NT + n0) >> 3;   // channel plane of f[0]
+            if (!SX && p.res != nullptr) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint4 r = rbuf[SX ? 0 : n0 / 8 + h];
+                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 g = unpack_h2(rr[i]);
+                  f[h * 8 + 2 * i] += g.x;
+                  f[h * 8 + 2 * i + 1] += g.y;
+                }
+              }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint4 o;
+              o.x = pack_h2(f[h * 8 + 0], f[h * 8 + 1]);
+              o.y = pack_h2(f[h * 8 + 2], f[h * 8 + 3]);
+              o.z = pack_h2(f[h * 8 + 4], f[h * 8 + 5]);
+              o.w = pack_h2(f[h * 8 + 6], f[h * 8 + 7]);
+              const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + cpl + h) * p.H + y) * p.W + x) * 8;
+              *reinterpret_cast<uint4*>(p.out + off) = o;
+            }
+          }
+        }
+      } else if constexpr (EPI == BIN_EPI_PIXSHUF) {
+        // out[c, 2y+i, 2x+j] = conv[4c+2i+j, y, x]   (nn.PixelShuffle(2), RDN.py:206)
+#pragma unroll 1
+        for (int n0 = 0; n0 < NT; n0 += 32) {
+          uint32_t v0[16], v1[16];
+          tmem_ld16(taddr + n0, v0);
+          tmem_ld16(taddr + n0 + 16, v1);
+          tmem_ld_wait();
+          if (valid) {
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              f[i] = __uint_as_float(v0[i]) + sbias[nh * NT + n0 + i];
+              f[16 + i] = __uint_as_float(v1[i]) + sbias[nh * NT + n0 + 16 + i];
+            }
+            const int opl = (nh * NT + n0) >> 5;   // output plane (8 channels = 32 conv channels)
+            const int H2 = 2 * p.H, W2 = 2 * p.W;
+#pragma unroll
+            for (int ij = 0; ij < 4; ++ij) {
+              uint4 o;
+              o.x = pack_h2(f[0 * 4 + ij], f[1 * 4 + ij]);
+              o.y = pack_h2(f[2 * 4 + ij], f[3 * 4 + ij]);
+              o.z = pack_h2(f[4 * 4 + ij], f[5 * 4 + ij]);
+              o.w = pack_h2(f[6 * 4 + ij], f[7 * 4 + ij]);
+              const int yy = 2 * y + (ij >> 1), xx = 2 * x + (ij & 1);
+              const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + opl) * H2 + yy) * W2 + xx) * 8;
+              *reinterpret_cast<uint4*>(p.out + off) = o;
+            }
+          }
+        }
+      } else {  // BIN_EPI_FINAL: fp32 NCHW = conv + bias + mean(frames)
+        float cv[3];
+        if constexpr (SX) {
+          uint32_t v0[16], v1[16], v2[16];
+          tmem_ld16(taddr, v0);
+          tmem_ld16(taddr + NT, v1);
+          tmem_ld16(taddr + 2 * NT, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[c]), 1);
+            const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c]), 2);
+            cv[c] = (__uint_as_float(v0[c]) + b1) + b2;
+          }
+        } else {
+          uint32_t v[16];
+          tmem_ld16(taddr, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 3; ++c) cv[c] = __uint_as_float(v[c]);
+        }
+        if (valid) {
+          const int call = b / p.fr.Bc, bb = b % p.fr.Bc;
+          const size_t hw = (size_t)p.H * p.W;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const size_t off = ((size_t)bb * 3 + c) * hw + (size_t)y * p.W + x;
+            p.fr.out[call][off] = (cv[c] + sbias[c]) + fmean[c];
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&ctrl->tmem_empty[as]);
+      if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 2);
     }
   }
 
@@ -430,6 +474,8 @@ int make_p8_tmap(CUtensorMap* m, const bin_act_t& t, int box_rows) {
   return BIN_OK;
 }
 
+long long* g_dbg = nullptr;   // perf-debug timeline buffer (tools only)
+
 static int num_sms() {
   static int n = []() {
     int dev = 0, v = 0;
@@ -471,15 +517,31 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
   p.resident = (p.nh == 1 && nchunks <= kMaxResidentChunks &&
                 kCtrlBytes + nchunks * C::W_CHUNK + 3 * C::A_BYTES + 256 <= kSmemMax) ? 1 : 0;
   const int res_bytes = p.resident ? nchunks * C::W_CHUNK : 0;
-  const int stage_bytes = C::A_BYTES + (p.resident ? 0 : C::W_STAGE);
-  int S = (kSmemMax - kCtrlBytes - res_bytes - 256) / stage_bytes;
+  const int unit_bytes = C::A_BYTES + (p.resident ? 0 : C::W_STAGE);
+  const int nunits = nchunks * C::NSUB;
+  // units per pipeline stage: an mbarrier round trip costs a few hundred cycles, so a stage should
+  // carry >= ~12 MMAs (>= ~700 tensor-pipe cycles); one 1x1 unit is only 4 MMAs.
+  const int mma_per_unit = kMT * C::TAPS_S * (kKC / 16);
+  int cps = (12 + mma_per_unit - 1) / mma_per_unit;
+  if (cps > nunits) cps = nunits;
+  const int avail = kSmemMax - kCtrlBytes - res_bytes - 256;
+  while (cps > 1 && avail / (cps * unit_bytes) < 2) --cps;
+  int S = avail / (cps * unit_bytes);
   if (S > kMaxStages) S = kMaxStages;
+  S &= ~1;                                     // even: producer i%2 must always see the same slots
   if (S < 2) return fail(BIN_ERR_UNSUPPORTED, "conv configuration does not fit in shared memory");
   p.nstages = S;
-  const int smem_bytes = kCtrlBytes + res_bytes + S * stage_bytes + 256;
+  p.cps = cps;
+  const int smem_bytes = kCtrlBytes + res_bytes + S * cps * unit_bytes + 256;
   p.out = reinterpret_cast<__half*>(a.out.ptr); p.out_planes = a.out.planes; p.out_plane0 = a.out_plane0;
   p.res = reinterpret_cast<const __half*>(a.res.ptr); p.res_planes = a.res.planes; p.res_plane0 = a.res_plane0;
   p.fr = a.fr;
+  { const char* e = getenv("BIN_B200_DEBUG"); p.debug = (e && *e) ? atoi(e) : 0; }   // perf experiments only
+  if (p.debug & 8) {
+    if (!g_dbg) { BIN_CUDA_OK(cudaMalloc(&g_dbg, 3 * 4096 * sizeof(long long))); }
+    BIN_CUDA_OK(cudaMemsetAsync(g_dbg, 0, 3 * 4096 * sizeof(long long), s));
+    p.dbg = g_dbg;
+  }
   auto kern = conv_igemm_kernel<NT, KS, EPI, SX>;
   static bool attr_done = false;   // per instantiation; idempotent, so a benign race at worst
   if (!attr_done) {
@@ -488,8 +550,18 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
   }
   int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
   if (grid < 1) return BIN_OK;
-  kern<<<grid, 256, smem_bytes, s>>>(p);
+  kern<<<grid, kThreads, smem_bytes, s>>>(p);
   BIN_CUDA_OK(cudaGetLastError());
+  if (p.debug & 16) {                       // debugging aid: synchronise and name the failing launch
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess)
+      return fail(BIN_ERR_CUDA, std::string("conv launch failed: ") + cudaGetErrorString(e) + " NT=" + std::to_string(NT) +
+                  " KS=" + std::to_string(KS) + " EPI=" + std::to_string(EPI) + " SX=" + std::to_string((int)SX) +
+                  " nch=" + std::to_string(p.nch0) + "+" + std::to_string(p.nch1) + " B/H/W=" + std::to_string(B) + "/" +
+                  std::to_string(H) + "/" + std::to_string(W) + " b0=" + std::to_string(p.b0) + " y0=" + std::to_string(p.y0) +
+                  " ny=" + std::to_string(p.ny) + " ntiles=" + std::to_string(p.ntiles) + " S=" + std::to_string(S) +
+                  " cps=" + std::to_string(cps) + " resident=" + std::to_string(p.resident));
+  }
   return BIN_OK;
 }
 

@@ -44,11 +44,13 @@ struct alignas(64) ConvParams {
   int H, W, Btot;                      // conv resolution
   int b0, y0, ny;                      // batch / row sub-range processed by this launch
   int tiles_x, tiles_y, ntiles, nh;    // nh = cout_pad / NT
-  int relu, resident, nstages;
+  int relu, resident, nstages, cps, debug;
   __half* out; int out_planes, out_plane0;
   const __half* res; int res_planes, res_plane0;
   bin_frames_t fr;
+  long long* dbg;
 };
+extern long long* g_dbg;
 
 int launch_conv(const bin_conv_args_t& a, cudaStream_t s);
 

@@ -144,6 +144,9 @@ int bin_pyramid3_fwd(const bin_net_t* net, const float* const* frames_host, floa
  * return cycles per MMA in *cycles_host (host pointer; synchronises). mode 0: A/B K-major
  * no-swizzle. */
 int bin_microbench_mma(int n, int iters, int mode, float* cycles_host);
+/* Perf tooling: with env BIN_B200_DEBUG=8 the conv kernel's block 0 records clock64 at role milestones
+ * ([role 0 producer,1 MMA,2 epilogue][iter][k] as 3x1024x4 int64); copies the last launch's timeline. */
+int bin_debug_timeline(long long* host, int n);
 
 #ifdef __cplusplus
 }

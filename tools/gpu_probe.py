@@ -87,7 +87,50 @@ def _conv_case(cin, cout, k, H, W, B=2, relu=False, res=False, epilogue=0, cin_s
     print(json.dumps({"max_abs_err": err, "ref_max": scale, "ok": bool(err <= 4e-3 * max(1.0, scale))}))
 
 
+def case_mmapat():
+    from bin_b200 import ops
+    res = {}
+    for vary in range(8):
+        res[f"A{'var' if vary & 1 else 'fix'}_B{'var' if vary & 2 else 'fix'}_{'data' if vary & 4 else 'zero'}"] = round(
+            ops.microbench_mma(96, 200, 0x1000 | vary), 2)
+    print(json.dumps(res))
+
+
+def case_sub(cin=128, k=3, cout=32):
+    import torch
+    import torch.nn.functional as F
+    from bin_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    B, H, W = 3, 56, 64
+    x = torch.randn(B, cin, H, W, device=dev)
+    w = torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, device=dev) * 0.1
+    ref = F.conv2d(x.half().float(), w.half().float(), b, padding=k // 2)
+    wp, bp = ops.pack_conv_weight(w, cout, cin), ops.pad_bias(b, cout)
+    in0 = ops.nchw_to_p8(x)
+    res = {}
+    for sub in [(0, 0, 0, 0), (1, 1, 0, 0), (0, 0, 11, 23), (2, 1, 30, 26), (1, 2, 5, 9)]:
+        out = torch.zeros((B, cout // 8, H, W, 8), dtype=torch.float16, device=dev)
+        for rep in range(20):
+            ops.conv_fwd(in0, wp, bp, k, cout, out=out, sub=sub)
+        torch.cuda.synchronize()
+        got = ops.p8_to_nchw(out, cout)
+        b0, nb, y0, ny = sub
+        nb = nb or B - b0
+        ny = ny or H - y0
+        mask = torch.zeros_like(ref)
+        mask[b0:b0 + nb, :, y0:y0 + ny] = 1
+        err = ((got - ref) * mask).abs().max().item()
+        outside = (got * (1 - mask)).abs().max().item()
+        res[str(sub)] = (round(err, 5), outside)
+    print(json.dumps(res))
+
+
 CASES = {
+    "mmapat": case_mmapat,
+    "sub3": lambda: case_sub(128, 3, 32),
+    "sub1": lambda: case_sub(224, 1, 96),
     "mma": case_mma,
     "c3_32_small": lambda: _conv_case(96, 32, 3, 8, 30, B=1),
     "c3_32": lambda: _conv_case(96, 32, 3, 20, 37, relu=True),
