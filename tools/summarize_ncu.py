@@ -1,0 +1,86 @@
+"""Turn the ncu artefacts in gpurun_out/ into the committed summaries under profiles/.
+usage: python tools/summarize_ncu.py r01"""
+import collections
+import csv
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+os.makedirs(P, exist_ok=True)
+
+
+def short(name):
+    m = re.search(r"conv_igemm_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(bool\)(\d)>", name)
+    if m:
+        epi = {"0": "P8", "1": "PIXSHUF", "2": "FINAL"}[m.group(3)]
+        return f"conv_igemm<NT={m.group(1)},KS={m.group(2)},{epi},SX={m.group(4)}>"
+    return re.sub(r"\(.*", "", name).replace("binb::", "")
+
+
+def launches():
+    path = os.path.join(G, "launches_window.csv")
+    if not os.path.exists(path):
+        return
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    agg = collections.OrderedDict()
+    tot = 0.0
+    for r in rows:
+        v = float(r["Metric Value"].replace(",", ""))
+        v = v / 1e3 if r["Metric Unit"] == "ns" else v * 1e3 if r["Metric Unit"] == "ms" else v
+        k = short(r["Kernel Name"])
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+        tot += v
+    with open(os.path.join(P, f"{tag}_launches_window.md"), "w") as f:
+        f.write(f"# {tag}: ncu launch list of ONE steady-state 6-frame 1280x720 window\n\n"
+                "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 869 -c 341 --csv python tools/run_window.py 2`\n"
+                "(BIN_B200_GRAPH=0; skip = 528 weight-pack launches + the 341 launches of window 0). Per-launch times under ncu are\n"
+                "cold-cache and serialised: compare SHARES, not absolutes.\n\n"
+                f"launches: {len(rows)}, sum of kernel durations: {tot/1e3:.2f} ms\n\n| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n")
+        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| {k} | {n} | {t:.1f} | {t/n:.1f} | {100*t/tot:.1f}% |\n")
+    print("wrote launches summary", len(rows), "launches")
+
+
+WANT = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
+        ("lts__t_sector_hit_rate.pct", "L2 hit %"), ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2->SM bytes"),
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+        ("sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active", "tensor(hmma) inst % of peak"),
+        ("TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "hmma cycles active (per TPC, 2 SMs)"),
+        ("sm__cycles_elapsed.max", "SM cycles elapsed"), ("launch__registers_per_thread", "regs/thread"),
+        ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("launch__shared_mem_per_block_dynamic", "dyn smem/CTA"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %")]
+
+
+def full(rep, title, note):
+    path = os.path.join(G, rep)
+    if not os.path.exists(path):
+        return
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    with open(os.path.join(P, f"{tag}_{rep.replace('.ncu-rep','')}.md"), "w") as f:
+        f.write(f"# {tag}: {title}\n\n{note}\n\n| metric | " + " | ".join(short(d[ix['Kernel Name']]) for d in data) + " |\n")
+        f.write("|---|" + "---|" * len(data) + "\n")
+        for m, label in WANT:
+            if m in ix:
+                f.write(f"| {label} [{units[ix[m]]}] | " + " | ".join(d[ix[m]][:12] for d in data) + " |\n")
+    print("wrote", rep)
+
+
+launches()
+full("prof_rdb5.ncu-rep", "ncu --set full: RDB 5 of the stage-1 launch (5 batched calls, 360x640): conv0..conv3 (x-stacked) + LFF",
+     "Command: `ncu --set full --clock-control none --import-source on -k regex:conv_igemm_kernel -s 357 -c 5 python tools/run_window.py 2`.\n"
+     "Algorithmic bytes per launch: conv c reads 5*230400*(192+64c) B and writes 5*230400*64 B; LFF reads 5*230400*640 B, writes 5*230400*192 B.\n"
+     "Algorithmic FLOPs per launch: 2*5*230400*(96+32c)*32*9 (conv c), 2*5*230400*224*96 (LFF).")
+full("prof_tail.ncu-rep", "ncu --set full: tail of the same stage: GFF.0, GFF.1, UPNet.0(+PixelShuffle), UPNet.2(+mean)",
+     "Command: `ncu --set full --clock-control none --import-source on -k regex:conv_igemm_kernel -s 392 -c 4 python tools/run_window.py 2`.")
