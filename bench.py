@@ -161,7 +161,9 @@ def dominant_kernel_roofline(torch, ops, pk, ncalls, h, w):
     ach = tot_flops / (tot_ms * 1e-3) / 1e12
     peak = pk["bf16_tflops"]
     return {"bound": "tensor", "kernel": "conv_igemm_kernel<32,3,P8,SX> (RDB 3x3 convs, 4 shapes)", "achieved": ach,
-            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": 1.5609e9 if (ncalls, h, w) == (5, 360, 640) else None,
+            "traffic_note": "dram__bytes_read+write summed over the 4 launches (profiles/r01_prof_rdb5.md); algorithmic bytes 1.622e9",
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({pk['source']}, burst: kernel timed alone)",
             "algorithmic_flops_per_launch_set": tot_flops, "ms_per_launch_set": tot_ms}
 

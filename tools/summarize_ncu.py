@@ -15,7 +15,7 @@ os.makedirs(P, exist_ok=True)
 
 
 def short(name):
-    m = re.search(r"conv_igemm_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(bool\)(\d)>", name)
+    m = re.search(r"conv_igemm_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d)>", name)
     if m:
         epi = {"0": "P8", "1": "PIXSHUF", "2": "FINAL"}[m.group(3)]
         return f"conv_igemm<NT={m.group(1)},KS={m.group(2)},{epi},SX={m.group(4)}>"
