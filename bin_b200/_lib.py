@@ -29,7 +29,7 @@ class ConvArgs(C.Structure):
                 ("in1", Act), ("in1_plane0", C.c_int), ("in1_planes", C.c_int),
                 ("w_packed", C.c_void_p), ("bias", C.c_void_p),
                 ("ksize", C.c_int), ("cout_pad", C.c_int), ("relu", C.c_int), ("epilogue", C.c_int), ("variant", C.c_int),
-                ("b_begin", C.c_int), ("b_count", C.c_int), ("y_begin", C.c_int), ("y_count", C.c_int),
+                ("b_begin", C.c_int), ("b_count", C.c_int), ("y_begin", C.c_int), ("y_count", C.c_int), ("store_planes", C.c_int),
                 ("out", Act), ("out_plane0", C.c_int),
                 ("res", Act), ("res_plane0", C.c_int),
                 ("fr", Frames)]
@@ -53,11 +53,23 @@ _SIGS = {
     "bin_packed_weight_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "bin_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bin_conv_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "bin_pack_conv_weight_t": (C.c_int, [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
+    "bin_conv_wgrad": (C.c_int, [Act, C.c_int, C.c_int, Act, C.c_int, C.c_int, Act, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "bin_convlstm_fwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 3 + [C.c_void_p]),
+    "bin_convlstm_bwd": (C.c_int, [C.c_void_p] * 13 + [C.c_int] * 3 + [C.c_void_p]),
     "bin_backbone_packed_bytes": (C.c_size_t, [C.c_int]),
     "bin_backbone_pack": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "bin_backbone_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "bin_backbone_fwd": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(Frames), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "bin_backbone_packed_t_bytes": (C.c_size_t, [C.c_int]),
+    "bin_backbone_pack_t": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "bin_backbone_train_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "bin_backbone_fwd_train": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(Frames), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "bin_backbone_grad_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
+    "bin_backbone_grad_param_floats": (C.c_size_t, [C.c_int]),
+    "bin_backbone_bwd": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(Frames), C.POINTER(Frames), C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bin_rdb_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                               C.c_void_p, C.c_size_t, C.c_void_p]),
     "bin_window_workspace_bytes": (C.c_size_t, [C.c_int] * 3),

@@ -27,6 +27,9 @@ int launch_pack_bias(const float* b, int cout, int cout_pad, float* dst, cudaStr
 int launch_convlstm(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
                     float* h_out, float* c_out, int B, int H, int W, cudaStream_t s);
 int run_mma_bench(int n, int iters, int mode, float* cycles_host);
+int launch_convlstm_bwd(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
+                        const float* dh, const float* dc, float* dgates_ws, float* dx, float* dc_prev, float* dh_prev,
+                        float* dw, float* db, int B, int H, int W, cudaStream_t s);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -84,7 +87,7 @@ struct BackboneWs {
   bin_act_t x0, f1, f2, cat, g, t1, t2, u;
   size_t bytes;
 };
-static BackboneWs backbone_ws(int nframes, int Btot, int H, int W, void* base) {
+static BackboneWs backbone_ws(int nframes, int Btot, int H, int W, void* base, bool train = false) {
   BackboneWs w;
   const int h = H / 2, wd = W / 2;
   size_t off = 0;
@@ -99,7 +102,7 @@ static BackboneWs backbone_ws(int nframes, int Btot, int H, int W, void* base) {
   w.f1 = carve(12, h, wd);
   w.f2 = carve(12, h, wd);
   w.cat = carve(12 * kD, h, wd);
-  w.g = carve(16, h, wd);
+  w.g = carve(train ? 16 * kD : 16, h, wd);   // training keeps the growth maps of all 12 RDBs for the backward
   w.t1 = carve(12, h, wd);
   w.t2 = carve(12, h, wd);
   w.u = carve(8, H, W);
@@ -188,16 +191,16 @@ static std::vector<Band> plan_bands(int Btot, int h, int w) {
 // One RDB: 4 x (conv3x3+ReLU -> growth planes) + LFF 1x1 + residual (RDN.py:149-165).
 static int run_rdb(const void* blob, const BackboneLayout& L, int i, const bin_act_t& xin, int x_plane0,
                    const bin_act_t& g, const bin_act_t& out, int out_plane0, const std::vector<Band>& bands,
-                   cudaStream_t s) {
+                   cudaStream_t s, int g_plane0 = 0) {
   const int base = 2 + i * (kCgrow + 1);
   const int h = xin.H;
   for (const Band& bd : bands) {
     for (int c = 0; c < kCgrow; ++c) {
       bin_conv_args_t a = conv_args(blob, L.conv[base + c]);
       a.in0 = xin; a.in0_plane0 = x_plane0; a.in0_planes = 12;
-      a.in1 = g; a.in1_plane0 = 0; a.in1_planes = 4 * c;
+      a.in1 = g; a.in1_plane0 = g_plane0; a.in1_planes = 4 * c;
       a.relu = 1; a.epilogue = BIN_EPI_P8;
-      a.out = g; a.out_plane0 = 4 * c;
+      a.out = g; a.out_plane0 = g_plane0 + 4 * c;
       const int ext = kCgrow - 1 - c;             // rows still needed by the convs downstream in this band
       const int lo = bd.y0 - ext < 0 ? 0 : bd.y0 - ext, hi = bd.y1 + ext > h ? h : bd.y1 + ext;
       a.b_begin = bd.b0; a.b_count = bd.nb; a.y_begin = lo; a.y_count = hi - lo;
@@ -205,7 +208,7 @@ static int run_rdb(const void* blob, const BackboneLayout& L, int i, const bin_a
     }
     bin_conv_args_t a = conv_args(blob, L.conv[base + kCgrow]);
     a.in0 = xin; a.in0_plane0 = x_plane0; a.in0_planes = 12;
-    a.in1 = g; a.in1_plane0 = 0; a.in1_planes = 16;
+    a.in1 = g; a.in1_plane0 = g_plane0; a.in1_planes = 16;
     a.epilogue = BIN_EPI_P8;
     a.out = out; a.out_plane0 = out_plane0;
     a.res = xin; a.res_plane0 = x_plane0;
@@ -216,13 +219,13 @@ static int run_rdb(const void* blob, const BackboneLayout& L, int i, const bin_a
 }
 
 static int run_backbone(int nframes, const void* blob, const bin_frames_t& fr, int H, int W, void* workspace,
-                        size_t workspace_bytes, cudaStream_t s) {
+                        size_t workspace_bytes, cudaStream_t s, bool train = false) {
   if (!valid_nframes(nframes) || fr.nframes != nframes) return fail(BIN_ERR_ARG, "backbone: nframes must be 2, 3 or 5");
   if (fr.ncalls < 1 || fr.ncalls > BIN_MAX_CALLS || fr.Bc < 1) return fail(BIN_ERR_ARG, "backbone: bad call table");
   if ((H & 1) || (W & 1) || H < 2 || W < 2) return fail(BIN_ERR_ARG, "backbone: H and W must be even (RDN.py:123-128)");
   const int Btot = fr.ncalls * fr.Bc;
   const BackboneLayout L = backbone_layout(nframes);
-  const BackboneWs ws = backbone_ws(nframes, Btot, H, W, workspace);
+  const BackboneWs ws = backbone_ws(nframes, Btot, H, W, workspace, train);
   if (ws.bytes > workspace_bytes) return fail(BIN_ERR_WORKSPACE, "backbone: workspace too small");
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(BIN_ERR_ARG, "backbone: workspace must be 256-byte aligned");
 
@@ -239,8 +242,9 @@ static int run_backbone(int nframes, const void* blob, const bin_frames_t& fr, i
   }
   const std::vector<Band> bands = plan_bands(Btot, H / 2, W / 2);
   for (int i = 0; i < kD; ++i) {                                                 // RDN.py:215-217
-    if (i == 0) BIN_TRY(run_rdb(blob, L, i, ws.f2, 0, ws.g, ws.cat, 0, bands, s));
-    else BIN_TRY(run_rdb(blob, L, i, ws.cat, 12 * (i - 1), ws.g, ws.cat, 12 * i, bands, s));
+    const int gp0 = train ? 16 * i : 0;
+    if (i == 0) BIN_TRY(run_rdb(blob, L, i, ws.f2, 0, ws.g, ws.cat, 0, bands, s, gp0));
+    else BIN_TRY(run_rdb(blob, L, i, ws.cat, 12 * (i - 1), ws.g, ws.cat, 12 * i, bands, s, gp0));
   }
   {
     bin_conv_args_t a = conv_args(blob, L.conv[62]);                             // GFF.0 on the 1152-ch concat (RDN.py:218)
@@ -263,6 +267,176 @@ static int run_backbone(int nframes, const void* blob, const bin_frames_t& fr, i
     BIN_TRY(launch_conv(a, s));
   }
   return BIN_OK;
+}
+
+// ------------------------------------------------------------------ backward of one backbone
+// Data gradients reuse conv_igemm_kernel: for a stride-1 / pad k/2 conv, dX = conv(dY, V) with
+// V[ci][co][ky][kx] = W[co][ci][k-1-ky][k-1-kx] (packed by launch_pack_weight_t, Cout' padded to a
+// multiple of 96 and clipped by store_planes).  Gradients are fp16 P8 tensors scaled by *scale (loss
+// scaling, a device scalar) and un-scaled when they leave the backbone (frame grads, dW, db).
+int launch_pack_weight_t(const float* w, int cout, int cin, int ks, int row0, int nrows, int cout_pad_t, int cin_pad_t,
+                         void* packed, cudaStream_t s);
+int launch_p8_add(const bin_act_t& dst, int dplane0, const bin_act_t& src, int splane0, int nplanes, cudaStream_t s);
+int launch_relu_mask(const bin_act_t& dg, int dplane0, const bin_act_t& g, int gplane0, int nplanes, cudaStream_t s);
+int launch_pixel_unshuffle(const bin_act_t& du, const bin_act_t& dst, cudaStream_t s);
+int launch_unpack_frames_grad(const bin_act_t& dx0, const bin_frames_t& dout, const bin_frames_t& dfr, int H, int W,
+                              const float* scale, cudaStream_t s);
+int launch_grad_out_to_p8(const bin_frames_t& dout, int H, int W, const bin_act_t& dst, const float* scale, cudaStream_t s);
+int launch_bias_grad(const bin_act_t& dy, int plane0, int C, const float* scale, float* db, cudaStream_t s);
+int launch_wgrad(const bin_act_t& x0, int x0_plane0, int x0_planes, const bin_act_t& x1, int x1_plane0, int x1_planes,
+                 const bin_act_t& dy, int dy_plane0, int cout, int cin, int ks, const float* scale, float* dw,
+                 cudaStream_t s);
+
+struct TSpec {          // one data-gradient conv: output rows [row0,row0+nrows) of the forward conv's Cin axis
+  int conv, row0, nrows, cout_pad_t, cin_pad_t, ks;
+  size_t off;
+};
+struct BackboneLayoutT {
+  TSpec x[BIN_BACKBONE_NCONV];      // x part / whole input
+  TSpec g[BIN_BACKBONE_NCONV];      // growth part (RDB convs c>=1 and LFF); nrows = 0 if absent
+  size_t zero_bias_off, bytes;
+};
+static BackboneLayoutT backbone_layout_t(int nframes) {
+  const BackboneLayout L = backbone_layout(nframes);
+  BackboneLayoutT T;
+  size_t off = 0;
+  auto mk = [&](int conv, int row0, int nrows) {
+    TSpec t;
+    t.conv = conv; t.row0 = row0; t.nrows = nrows; t.ks = L.conv[conv].ks;
+    t.cout_pad_t = nrows > 0 ? (int)align_up(nrows, 96) : 0;
+    t.cin_pad_t = (int)align_up(L.conv[conv].cout, kKC);
+    t.off = off;
+    if (nrows > 0) off = align_up(off + (size_t)t.cout_pad_t * t.cin_pad_t * t.ks * t.ks * sizeof(__half), 256);
+    return t;
+  };
+  for (int i = 0; i < BIN_BACKBONE_NCONV; ++i) {
+    const ConvSpec& c = L.conv[i];
+    const bool in_rdb = i >= 2 && i < 2 + kD * (kCgrow + 1);
+    if (in_rdb) {
+      T.x[i] = mk(i, 0, kG0);
+      T.g[i] = mk(i, kG0, c.cin - kG0);          // 0 rows for conv 0 of each RDB
+    } else {
+      T.x[i] = mk(i, 0, c.cin);
+      T.g[i] = mk(i, 0, 0);
+    }
+  }
+  T.zero_bias_off = off;
+  off = align_up(off + 1152 * sizeof(float), 256);
+  T.bytes = off;
+  return T;
+}
+
+struct GradWs {
+  bin_act_t dout16, du, dup0, dt2, dt1, dcat, df2, dg, dx0;
+  size_t bytes;
+};
+static GradWs grad_ws(int nframes, int Btot, int H, int W, void* base) {
+  GradWs w;
+  const int h = H / 2, wd = W / 2;
+  size_t off = 0;
+  auto carve = [&](int planes, int hh, int ww) {
+    bin_act_t t;
+    t.ptr = base ? (void*)((uint8_t*)base + off) : nullptr;
+    t.B = Btot; t.planes = planes; t.H = hh; t.W = ww;
+    off = align_up(off + (size_t)Btot * planes * hh * ww * 16, 256);
+    return t;
+  };
+  w.dout16 = carve(4, H, W);
+  w.du = carve(8, H, W);
+  w.dup0 = carve(32, h, wd);
+  w.dt2 = carve(12, h, wd);
+  w.dt1 = carve(12, h, wd);
+  w.dcat = carve(12 * kD, h, wd);
+  w.df2 = carve(12, h, wd);
+  w.dg = carve(16, h, wd);
+  w.dx0 = carve((int)align_up(12 * nframes, kKC) / 8, h, wd);
+  w.bytes = off;
+  return w;
+}
+
+struct GradParamLayout { size_t w[BIN_BACKBONE_NCONV], b[BIN_BACKBONE_NCONV], floats; };
+static GradParamLayout grad_param_layout(int nframes) {
+  const BackboneLayout L = backbone_layout(nframes);
+  GradParamLayout g;
+  size_t off = 0;
+  for (int i = 0; i < BIN_BACKBONE_NCONV; ++i) {
+    g.w[i] = off; off += (size_t)L.conv[i].cout * L.conv[i].cin * L.conv[i].ks * L.conv[i].ks;
+    g.b[i] = off; off += (size_t)L.conv[i].cout;
+  }
+  g.floats = off;
+  return g;
+}
+
+static int run_backbone_bwd(int nframes, const void* blob_t, const bin_frames_t& dout, const bin_frames_t& dfr, int H,
+                            int W, const void* save_ws, void* gws_ptr, size_t gws_bytes, float* gparams,
+                            const float* scale, cudaStream_t s) {
+  if (!valid_nframes(nframes) || dfr.nframes != nframes) return fail(BIN_ERR_ARG, "backbone_bwd: nframes must be 2, 3 or 5");
+  if (dout.ncalls != dfr.ncalls || dout.Bc != dfr.Bc || dout.ncalls < 1 || dout.ncalls > BIN_MAX_CALLS)
+    return fail(BIN_ERR_ARG, "backbone_bwd: bad call tables");
+  const int Btot = dout.ncalls * dout.Bc;
+  const BackboneLayout L = backbone_layout(nframes);
+  const BackboneLayoutT T = backbone_layout_t(nframes);
+  const GradParamLayout GP = grad_param_layout(nframes);
+  const BackboneWs ws = backbone_ws(nframes, Btot, H, W, const_cast<void*>(save_ws), true);
+  const GradWs gw = grad_ws(nframes, Btot, H, W, gws_ptr);
+  if (gw.bytes > gws_bytes) return fail(BIN_ERR_WORKSPACE, "backbone_bwd: gradient workspace too small");
+  const float* zero_bias = (const float*)((const uint8_t*)blob_t + T.zero_bias_off);
+
+  // dX (+)= conv(dY planes [dy_plane0, +dy_planes), V): writes `nstore` planes of `out` at out_plane0
+  auto dgrad = [&](const TSpec& t, const bin_act_t& dy, int dy_plane0, int dy_planes, const bin_act_t& out, int out_plane0,
+                   int nstore, bool accumulate) -> int {
+    bin_conv_args_t a;
+    memset(&a, 0, sizeof(a));
+    a.in0 = dy; a.in0_plane0 = dy_plane0; a.in0_planes = dy_planes;
+    a.w_packed = (const uint8_t*)blob_t + t.off; a.bias = zero_bias;
+    a.ksize = t.ks; a.cout_pad = t.cout_pad_t; a.epilogue = BIN_EPI_P8;
+    a.out = out; a.out_plane0 = out_plane0; a.store_planes = nstore;
+    if (accumulate) { a.res = out; a.res_plane0 = out_plane0; }
+    return launch_conv(a, s);
+  };
+  // dW += X^T dY, db += sum dY for forward conv `idx`
+  auto wgrad = [&](int idx, const bin_act_t& x0, int x0p, int x0n, const bin_act_t& x1, int x1p, int x1n,
+                   const bin_act_t& dy, int dyp) -> int {
+    const ConvSpec& c = L.conv[idx];
+    BIN_TRY(launch_bias_grad(dy, dyp, c.cout, scale, gparams + GP.b[idx], s));
+    return launch_wgrad(x0, x0p, x0n, x1, x1p, x1n, dy, dyp, c.cout, c.cin, c.ks, scale, gparams + GP.w[idx], s);
+  };
+  const bin_act_t none = {nullptr, 0, 0, 0, 0};
+
+  BIN_TRY(launch_grad_out_to_p8(dout, H, W, gw.dout16, scale, s));
+  BIN_TRY(wgrad(65, ws.u, 0, 8, none, 0, 0, gw.dout16, 0));                          // UPNet.2
+  BIN_TRY(dgrad(T.x[65], gw.dout16, 0, 4, gw.du, 0, 8, false));
+  BIN_TRY(launch_pixel_unshuffle(gw.du, gw.dup0, s));                               // nn.PixelShuffle backward
+  BIN_TRY(wgrad(64, ws.t2, 0, 12, none, 0, 0, gw.dup0, 0));                          // UPNet.0
+  BIN_TRY(dgrad(T.x[64], gw.dup0, 0, 32, gw.dt2, 0, 12, false));
+  BIN_TRY(wgrad(63, ws.t1, 0, 12, none, 0, 0, gw.dt2, 0));                           // GFF.1
+  BIN_TRY(dgrad(T.x[63], gw.dt2, 0, 12, gw.dt1, 0, 12, false));                      // dt2 doubles as d f__1 (RDN.py:219)
+  BIN_TRY(wgrad(62, ws.cat, 0, 12 * kD, none, 0, 0, gw.dt1, 0));                     // GFF.0
+  BIN_TRY(dgrad(T.x[62], gw.dt1, 0, 12, gw.dcat, 0, 12 * kD, false));
+  BIN_CUDA_OK(cudaMemsetAsync(gw.df2.ptr, 0, (size_t)Btot * 12 * (H / 2) * (W / 2) * 16, s));
+  for (int i = kD - 1; i >= 0; --i) {
+    const int base = 2 + i * (kCgrow + 1);
+    const bin_act_t& xin = i == 0 ? ws.f2 : ws.cat;           // forward input of RDB i
+    const int xin_p = i == 0 ? 0 : 12 * (i - 1);
+    const bin_act_t& dxin = i == 0 ? gw.df2 : gw.dcat;        // its gradient (accumulated)
+    const int dxin_p = i == 0 ? 0 : 12 * (i - 1);
+    const int dxo_p = 12 * i;                                 // d x_{i+1}, complete at this point
+    BIN_TRY(wgrad(base + kCgrow, xin, xin_p, 12, ws.g, 16 * i, 16, gw.dcat, dxo_p));                 // LFF
+    BIN_TRY(launch_p8_add(dxin, dxin_p, gw.dcat, dxo_p, 12, s));                                      // residual (RDN.py:165)
+    BIN_TRY(dgrad(T.x[base + kCgrow], gw.dcat, dxo_p, 12, dxin, dxin_p, 12, true));
+    BIN_TRY(dgrad(T.g[base + kCgrow], gw.dcat, dxo_p, 12, gw.dg, 0, 16, false));
+    for (int c = kCgrow - 1; c >= 0; --c) {
+      BIN_TRY(launch_relu_mask(gw.dg, 4 * c, ws.g, 16 * i + 4 * c, 4, s));                            // RDN.py:142
+      BIN_TRY(wgrad(base + c, xin, xin_p, 12, ws.g, 16 * i, 4 * c, gw.dg, 4 * c));
+      BIN_TRY(dgrad(T.x[base + c], gw.dg, 4 * c, 4, dxin, dxin_p, 12, true));
+      if (c > 0) BIN_TRY(dgrad(T.g[base + c], gw.dg, 4 * c, 4, gw.dg, 0, 4 * c, true));
+    }
+  }
+  BIN_TRY(wgrad(1, ws.f1, 0, 12, none, 0, 0, gw.df2, 0));                            // SFENet2
+  BIN_TRY(dgrad(T.x[1], gw.df2, 0, 12, gw.dt2, 0, 12, true));                        // d f__1 complete
+  BIN_TRY(wgrad(0, ws.x0, 0, ws.x0.planes, none, 0, 0, gw.dt2, 0));                  // SFENet1
+  BIN_TRY(dgrad(T.x[0], gw.dt2, 0, 12, gw.dx0, 0, gw.dx0.planes, false));
+  return launch_unpack_frames_grad(gw.dx0, dout, dfr, H, W, scale, s);
 }
 
 // ------------------------------------------------------------------ window orchestration
@@ -328,6 +502,15 @@ int bin_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int 
                          void* packed, bin_stream_t s) {
   return launch_pack_weight(w_oihw, cout, cin, ksize, cout_pad, cin_pad, variant, packed, (cudaStream_t)s);
 }
+int bin_pack_conv_weight_t(const float* w_oihw, int cout, int cin, int ksize, int row0, int nrows, int cout_pad_t,
+                           int cin_pad_t, void* packed, bin_stream_t s) {
+  return launch_pack_weight_t(w_oihw, cout, cin, ksize, row0, nrows, cout_pad_t, cin_pad_t, packed, (cudaStream_t)s);
+}
+int bin_conv_wgrad(bin_act_t x0, int x0_plane0, int x0_planes, bin_act_t x1, int x1_plane0, int x1_planes, bin_act_t dy,
+                   int dy_plane0, int cout, int cin, int ksize, const float* scale_dev, float* dw, bin_stream_t s) {
+  return launch_wgrad(x0, x0_plane0, x0_planes, x1, x1_plane0, x1_planes, dy, dy_plane0, cout, cin, ksize, scale_dev, dw,
+                      (cudaStream_t)s);
+}
 int bin_conv_fwd(const bin_conv_args_t* a, bin_stream_t s) {
   if (!a) return fail(BIN_ERR_ARG, "conv: null args");
   return launch_conv(*a, (cudaStream_t)s);
@@ -335,6 +518,13 @@ int bin_conv_fwd(const bin_conv_args_t* a, bin_stream_t s) {
 int bin_convlstm_fwd(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
                      float* h_out, float* c_out, int B, int H, int W, bin_stream_t s) {
   return launch_convlstm(x, c_prev, h_prev, w, b, h_out, c_out, B, H, W, (cudaStream_t)s);
+}
+
+int bin_convlstm_bwd(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
+                     const float* dh, const float* dc, float* dgates_ws, float* dx, float* dc_prev, float* dh_prev,
+                     float* dw, float* db, int B, int H, int W, bin_stream_t s) {
+  if (!x || !w || !b || !dgates_ws || !dx || !dw || !db) return fail(BIN_ERR_ARG, "convlstm_bwd: null argument");
+  return launch_convlstm_bwd(x, c_prev, h_prev, w, b, dh, dc, dgates_ws, dx, dc_prev, dh_prev, dw, db, B, H, W, (cudaStream_t)s);
 }
 
 size_t bin_backbone_packed_bytes(int nframes) { return valid_nframes(nframes) ? backbone_layout(nframes).bytes : 0; }
@@ -361,6 +551,46 @@ int bin_backbone_fwd(int nframes, const void* blob, const bin_frames_t* fr, int 
                      size_t workspace_bytes, bin_stream_t s) {
   if (!fr || !blob) return fail(BIN_ERR_ARG, "backbone_fwd: null argument");
   return run_backbone(nframes, blob, *fr, H, W, workspace, workspace_bytes, (cudaStream_t)s);
+}
+
+size_t bin_backbone_packed_t_bytes(int nframes) { return valid_nframes(nframes) ? backbone_layout_t(nframes).bytes : 0; }
+
+int bin_backbone_pack_t(int nframes, const float* const* w_host, void* blob_t, bin_stream_t s) {
+  if (!valid_nframes(nframes)) return fail(BIN_ERR_ARG, "backbone_pack_t: nframes must be 2, 3 or 5");
+  const BackboneLayout L = backbone_layout(nframes);
+  const BackboneLayoutT T = backbone_layout_t(nframes);
+  for (int i = 0; i < BIN_BACKBONE_NCONV; ++i) {
+    const ConvSpec& c = L.conv[i];
+    const TSpec* parts[2] = {&T.x[i], &T.g[i]};
+    for (const TSpec* t : parts) {
+      if (t->nrows <= 0) continue;
+      BIN_TRY(launch_pack_weight_t(w_host[i], c.cout, c.cin, c.ks, t->row0, t->nrows, t->cout_pad_t, t->cin_pad_t,
+                                   (uint8_t*)blob_t + t->off, (cudaStream_t)s));
+    }
+  }
+  BIN_CUDA_OK(cudaMemsetAsync((uint8_t*)blob_t + T.zero_bias_off, 0, 1152 * sizeof(float), (cudaStream_t)s));
+  return BIN_OK;
+}
+
+size_t bin_backbone_train_workspace_bytes(int nframes, int Btot, int H, int W) {
+  return valid_nframes(nframes) ? backbone_ws(nframes, Btot, H, W, nullptr, true).bytes : 0;
+}
+int bin_backbone_fwd_train(int nframes, const void* blob, const bin_frames_t* fr, int H, int W, void* save_ws,
+                           size_t save_ws_bytes, bin_stream_t s) {
+  if (!fr || !blob) return fail(BIN_ERR_ARG, "backbone_fwd_train: null argument");
+  return run_backbone(nframes, blob, *fr, H, W, save_ws, save_ws_bytes, (cudaStream_t)s, true);
+}
+size_t bin_backbone_grad_workspace_bytes(int nframes, int Btot, int H, int W) {
+  return valid_nframes(nframes) ? grad_ws(nframes, Btot, H, W, nullptr).bytes : 0;
+}
+size_t bin_backbone_grad_param_floats(int nframes) { return valid_nframes(nframes) ? grad_param_layout(nframes).floats : 0; }
+int bin_backbone_bwd(int nframes, const void* blob_t, const bin_frames_t* dout, const bin_frames_t* dframes, int H, int W,
+                     const void* save_ws, void* grad_ws_ptr, size_t grad_ws_bytes, float* grad_params,
+                     const float* scale_dev, bin_stream_t s) {
+  if (!blob_t || !dout || !dframes || !save_ws || !grad_params || !scale_dev)
+    return fail(BIN_ERR_ARG, "backbone_bwd: null argument");
+  return run_backbone_bwd(nframes, blob_t, *dout, *dframes, H, W, save_ws, grad_ws_ptr, grad_ws_bytes, grad_params,
+                          scale_dev, (cudaStream_t)s);
 }
 
 int bin_rdb_fwd(const void* blob, int nframes, int index, const float* x, float* y, int B, int h, int w,

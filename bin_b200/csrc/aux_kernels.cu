@@ -77,9 +77,12 @@ __global__ void pack_frames_kernel(const __grid_constant__ bin_frames_t fr, int 
 }
 
 // ------------------------------------------------------------------ weight packer
-// OIHW fp32 -> [nh][chunk][ky][kx][4][NT][8] fp16, or (stackx) [chunk][ky][4][kx*cout_pad+co][8]
+// OIHW fp32 -> [nh][chunk][ky][kx][4][NT][8] fp16, or (stackx) [chunk][ky][4][kx*cout_pad+co][8].
+// transpose != 0 packs the data-gradient weights instead: V[co'][ci'][ky][kx] = W[ci'][row0+co'][k-1-ky][k-1-kx]
+// (a conv with V over dY gives dX for stride-1 / pad k/2 convs), co' < nrows, ci' < cout.
 __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, int ks, int cout_pad, int cin_pad,
-                                   int nt, int stackx, __half* __restrict__ dst) {
+                                   int nt, int stackx, int transpose, int row0, int nrows,
+                                   __half* __restrict__ dst) {
   const size_t total = (size_t)cout_pad * cin_pad * ks * ks;
   const int nchunks = cin_pad / kKC;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -102,8 +105,145 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
     }
     const int ci = ch * kKC + kp * 8 + e;
     float v = 0.f;
-    if (co < cout && ci < cin) v = w[(((size_t)co * cin + ci) * ks + ky) * ks + kx];
+    if (!transpose) {
+      if (co < cout && ci < cin) v = w[(((size_t)co * cin + ci) * ks + ky) * ks + kx];
+    } else {
+      if (co < nrows && ci < cout) v = w[(((size_t)ci * cin + row0 + co) * ks + (ks - 1 - ky)) * ks + (ks - 1 - kx)];
+    }
     dst[i] = __float2half_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------ element-wise helpers of the backward pass
+// dst += src on P8 plane ranges (fp16).
+__global__ void p8_add_kernel(__half* __restrict__ dst, int dplanes, int dplane0, const __half* __restrict__ src,
+                              int splanes, int splane0, int nplanes, int B, size_t hw) {
+  const size_t total = (size_t)B * nplanes * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t px = i % hw;
+    const int pl = (i / hw) % nplanes;
+    const int b = i / (hw * nplanes);
+    uint4* d = reinterpret_cast<uint4*>(dst + (((size_t)b * dplanes + dplane0 + pl) * hw + px) * 8);
+    const uint4 sv = *reinterpret_cast<const uint4*>(src + (((size_t)b * splanes + splane0 + pl) * hw + px) * 8);
+    uint4 dv = *d;
+    __half2* dh = reinterpret_cast<__half2*>(&dv);
+    const __half2* sh = reinterpret_cast<const __half2*>(&sv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dh[k] = __hadd2(dh[k], sh[k]);
+    *d = dv;
+  }
+}
+// ReLU backward: dg *= (g > 0), both P8 plane ranges.
+__global__ void p8_relu_mask_kernel(__half* __restrict__ dg, int dplanes, int dplane0, const __half* __restrict__ g,
+                                    int gplanes, int gplane0, int nplanes, int B, size_t hw) {
+  const size_t total = (size_t)B * nplanes * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t px = i % hw;
+    const int pl = (i / hw) % nplanes;
+    const int b = i / (hw * nplanes);
+    uint4* d = reinterpret_cast<uint4*>(dg + (((size_t)b * dplanes + dplane0 + pl) * hw + px) * 8);
+    const uint4 gv = *reinterpret_cast<const uint4*>(g + (((size_t)b * gplanes + gplane0 + pl) * hw + px) * 8);
+    uint4 dv = *d;
+    __half* dh = reinterpret_cast<__half*>(&dv);
+    const __half* gh = reinterpret_cast<const __half*>(&gv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (!(__half2float(gh[k]) > 0.f)) dh[k] = __float2half_rn(0.f);
+    *d = dv;
+  }
+}
+// PixelShuffle(2) backward: dU P8 (B, 8 planes, 2h, 2w) -> d(conv out) P8 (B, 32 planes, h, w), n = 4c+2i+j.
+__global__ void pixel_unshuffle_kernel(const __half* __restrict__ du, __half* __restrict__ dst, int B, int h, int w) {
+  const size_t total = (size_t)B * 32 * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = i % w;
+    const int y = (i / w) % h;
+    const int pl = (i / ((size_t)w * h)) % 32;      // output plane: channels n = pl*8 .. pl*8+7
+    const int b = i / ((size_t)w * h * 32);
+    __align__(16) __half v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int n = pl * 8 + e, c = n >> 2, ii = (n >> 1) & 1, jj = n & 1;
+      v[e] = du[((((size_t)b * 8 + (c >> 3)) * (2 * h) + 2 * y + ii) * (2 * w) + 2 * x + jj) * 8 + (c & 7)];
+    }
+    *reinterpret_cast<uint4*>(dst + ((((size_t)b * 32 + pl) * h + y) * w + x) * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+// Backward of pack_frames + of the final "+ mean(frames)": for call k, frame f (fp32 NCHW):
+//   dframe = inv_scale * depth_to_space(dX0 channels of frame f) + dOut / nframes
+__global__ void unpack_frames_grad_kernel(const __half* __restrict__ dx0, int planes, const __grid_constant__ bin_frames_t dout,
+                                          const __grid_constant__ bin_frames_t dfr, int H, int W, const float* __restrict__ scale) {
+  const int h = H / 2, w = W / 2;
+  const int Btot = dfr.ncalls * dfr.Bc;
+  const size_t total = (size_t)Btot * dfr.nframes * 3 * h * w;
+  const float inv = 1.f / scale[0];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = i % w;
+    const int y = (i / w) % h;
+    const int rgb = (i / ((size_t)w * h)) % 3;
+    const int f = (i / ((size_t)w * h * 3)) % dfr.nframes;
+    const int b = i / ((size_t)w * h * 3 * dfr.nframes);
+    const int call = b / dfr.Bc, bb = b % dfr.Bc;
+    const int c4 = (f * 3 + rgb) * 4;                 // packed channels c4..c4+3 = (dy,dx) of this (frame,rgb)
+    const __half* src = dx0 + ((((size_t)b * planes + (c4 >> 3)) * h + y) * w + x) * 8 + (c4 & 7);
+    const float* go = dout.out[call] + (((size_t)bb * 3 + rgb) * H + 2 * y) * W + 2 * x;
+    float* dst = const_cast<float*>(dfr.frame[call][f]) + (((size_t)bb * 3 + rgb) * H + 2 * y) * W + 2 * x;
+    const float rn = 1.f / (float)dfr.nframes;
+    dst[0] = __half2float(src[0]) * inv + go[0] * rn;
+    dst[1] = __half2float(src[1]) * inv + go[1] * rn;
+    dst[W] = __half2float(src[2]) * inv + go[W] * rn;
+    dst[W + 1] = __half2float(src[3]) * inv + go[W + 1] * rn;
+  }
+}
+// dOut (fp32 NCHW, per call) * scale -> P8 (Btot, 4 planes, H, W), channels 3..31 zero.
+__global__ void grad_out_to_p8_kernel(const __grid_constant__ bin_frames_t dout, int H, int W, __half* __restrict__ dst,
+                                      const float* __restrict__ scale) {
+  const int Btot = dout.ncalls * dout.Bc;
+  const size_t hw = (size_t)H * W;
+  const size_t total = (size_t)Btot * 4 * hw;
+  const float sc = scale[0];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t px = i % hw;
+    const int pl = (i / hw) % 4;
+    const int b = i / (hw * 4);
+    const int call = b / dout.Bc, bb = b % dout.Bc;
+    __align__(16) __half v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __float2half_rn(0.f);
+    if (pl == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = __float2half_rn(dout.out[call][((size_t)bb * 3 + c) * hw + px] * sc);
+    }
+    *reinterpret_cast<uint4*>(dst + (((size_t)b * 4 + pl) * hw + px) * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+// db[c] += inv_scale * sum over (B, H, W) of dY[c] for P8 planes [plane0, plane0+ceil(C/8)).
+__global__ void p8_bias_grad_kernel(const __half* __restrict__ dy, int planes, int plane0, int C, int B, size_t hw,
+                                    const float* __restrict__ scale, float* __restrict__ db) {
+  __shared__ float part[8][8];
+  const int pl = blockIdx.y;                        // plane within the range
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const size_t total = (size_t)B * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t px = i % hw;
+    const int b = i / hw;
+    const uint4 v = *reinterpret_cast<const uint4*>(dy + (((size_t)b * planes + plane0 + pl) * hw + px) * 8);
+    const __half* h8 = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += __half2float(h8[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+    for (int k = 0; k < 8; ++k) part[warp][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.f;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += part[wv][threadIdx.x];
+    const int c = pl * 8 + threadIdx.x;
+    if (c < C) atomicAdd(db + c, s / scale[0]);
   }
 }
 
@@ -160,6 +300,135 @@ __global__ void convlstm_kernel(const float* __restrict__ x, const float* __rest
       const size_t off = ((size_t)b * 3 + c) * hw + (size_t)y * W + xw;
       h_out[off] = hn;
       if (c_out) c_out[off] = cn;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ ConvLSTMCell backward (fp32)
+// Pass 1 (per pixel): recompute the gates (RDN.py:74-82), write d(gate pre-activations) [B,12,H,W] and dc_prev.
+__global__ void convlstm_bwd_gates_kernel(const float* __restrict__ x, const float* __restrict__ c_prev,
+                                          const float* __restrict__ h_prev, const float* __restrict__ w,
+                                          const float* __restrict__ bias, const float* __restrict__ dh,
+                                          const float* __restrict__ dc, float* __restrict__ dgates,
+                                          float* __restrict__ dc_prev, int B, int H, int W) {
+  __shared__ float sw[12 * 6 * 9];
+  __shared__ float sb[12];
+  for (int i = threadIdx.x; i < 12 * 6 * 9; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 12) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const size_t hw = (size_t)H * W;
+  const size_t total = (size_t)B * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xw = i % W;
+    const int y = (i / W) % H;
+    const int b = i / hw;
+    float g[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) g[k] = sb[k];
+    const int nin = h_prev ? 6 : 3;
+    for (int c = 0; c < nin; ++c) {
+      const float* src = (c < 3 ? x + ((size_t)b * 3 + c) * hw : h_prev + ((size_t)b * 3 + (c - 3)) * hw);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = xw + kx - 1;
+          if (xx < 0 || xx >= W) continue;
+          const float v = src[(size_t)yy * W + xx];
+#pragma unroll
+          for (int k = 0; k < 12; ++k) g[k] = fmaf(sw[(k * 6 + c) * 9 + ky * 3 + kx], v, g[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const size_t off = ((size_t)b * 3 + c) * hw + (size_t)y * W + xw;
+      const float cp = c_prev ? c_prev[off] : 0.f;
+      const float si = 1.f / (1.f + expf(-g[c]));
+      const float tj = tanhf(g[3 + c]);
+      const float sf = 1.f / (1.f + expf(-(g[6 + c] + 1.0f)));
+      const float so = 1.f / (1.f + expf(-g[9 + c]));
+      const float cn = cp * sf + si * tj;
+      const float tc = tanhf(cn);
+      const float dhv = dh ? dh[off] : 0.f;
+      const float dct = (dc ? dc[off] : 0.f) + dhv * so * (1.f - tc * tc);
+      const size_t gb = ((size_t)b * 12) * hw + (size_t)y * W + xw;
+      dgates[gb + (size_t)(0 + c) * hw] = dct * tj * si * (1.f - si);          // d i
+      dgates[gb + (size_t)(3 + c) * hw] = dct * si * (1.f - tj * tj);          // d j
+      dgates[gb + (size_t)(6 + c) * hw] = dct * cp * sf * (1.f - sf);          // d f
+      dgates[gb + (size_t)(9 + c) * hw] = dhv * tc * so * (1.f - so);          // d o
+      if (dc_prev) dc_prev[off] = dct * sf;
+    }
+  }
+}
+// Pass 2: dW[k][c][tap] += sum_p dgates[k][p] * in[c][p+off], db[k] += sum_p dgates[k][p]  (660 outputs).
+__global__ void convlstm_bwd_weights_kernel(const float* __restrict__ x, const float* __restrict__ h_prev,
+                                            const float* __restrict__ dgates, float* __restrict__ dw,
+                                            float* __restrict__ db, int B, int H, int W, int chunk) {
+  const size_t hw = (size_t)H * W;
+  const size_t total = (size_t)B * hw;
+  const size_t p0 = (size_t)blockIdx.x * chunk;
+  const size_t p1 = p0 + chunk < total ? p0 + chunk : total;
+  for (int o = threadIdx.x; o < 660; o += blockDim.x) {
+    float acc = 0.f;
+    if (o < 648) {
+      const int k = o / 54, c = (o / 9) % 6, tap = o % 9, ky = tap / 3 - 1, kx = tap % 3 - 1;
+      if (c < 3 || h_prev) {
+        const float* src = c < 3 ? x : h_prev;
+        const int cc = c < 3 ? c : c - 3;
+        for (size_t p = p0; p < p1; ++p) {
+          const int xw = p % W, y = (p / W) % H, b = p / hw;
+          const int yy = y + ky, xx = xw + kx;
+          if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+          acc = fmaf(dgates[((size_t)b * 12 + k) * hw + (size_t)y * W + xw], src[((size_t)b * 3 + cc) * hw + (size_t)yy * W + xx], acc);
+        }
+      }
+      atomicAdd(dw + o, acc);
+    } else {
+      const int k = o - 648;
+      for (size_t p = p0; p < p1; ++p) {
+        const int b = p / hw;
+        acc += dgates[((size_t)b * 12 + k) * hw + (p % hw)];
+      }
+      atomicAdd(db + k, acc);
+    }
+  }
+}
+// Pass 3: dx[c][q] = sum_{k,tap} W[k][c][tap] * dgates[k][q - off(tap)]  (and dh_prev for c = 3..5).
+__global__ void convlstm_bwd_input_kernel(const float* __restrict__ dgates, const float* __restrict__ w,
+                                          float* __restrict__ dx, float* __restrict__ dh_prev, int B, int H, int W) {
+  __shared__ float sw[12 * 6 * 9];
+  for (int i = threadIdx.x; i < 12 * 6 * 9; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const size_t hw = (size_t)H * W;
+  const size_t total = (size_t)B * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xw = i % W;
+    const int y = (i / W) % H;
+    const int b = i / hw;
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y - (ky - 1);                       // output pixel that read this input through tap (ky,kx)
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = xw - (kx - 1);
+        if (xx < 0 || xx >= W) continue;
+        for (int k = 0; k < 12; ++k) {
+          const float d = dgates[((size_t)b * 12 + k) * hw + (size_t)yy * W + xx];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) acc[c] = fmaf(sw[(k * 6 + c) * 9 + ky * 3 + kx], d, acc[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const size_t off = ((size_t)b * 3 + c) * hw + (size_t)y * W + xw;
+      dx[off] = acc[c];
+      if (dh_prev) dh_prev[off] = acc[3 + c];
     }
   }
 }
@@ -343,10 +612,22 @@ int launch_pack_weight(const float* w, int cout, int cin, int ks, int cout_pad, 
   if (cin_pad % kKC || cout_pad % 16 || cout > cout_pad || cin > cin_pad)
     return fail(BIN_ERR_ARG, "pack_conv_weight: cin_pad must be a multiple of 32, cout_pad of 16");
   const int nt = conv_nt(cout_pad);
-  if (cout_pad % nt) return fail(BIN_ERR_ARG, "pack_conv_weight: cout_pad must be <=128 or a multiple of 128");
+  if (cout_pad % nt) return fail(BIN_ERR_ARG, "pack_conv_weight: cout_pad must be <=128, or a multiple of 96 or 128");
   const size_t total = (size_t)cout_pad * cin_pad * ks * ks;
   const int stackx = (ks == 3 && (cout_pad == 32 || cout_pad == 16) && variant == BIN_CONV_DEFAULT) ? 1 : 0;
-  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, cout, cin, ks, cout_pad, cin_pad, nt, stackx,
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, cout, cin, ks, cout_pad, cin_pad, nt, stackx, 0, 0, 0,
+                                                          (__half*)packed);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+// data-gradient weights of a conv (cout,cin,ks): output rows [row0,row0+nrows) of the cin axis, padded to
+// cout_pad_t (multiple of 96); K = cout padded to cin_pad_t (multiple of 32).
+int launch_pack_weight_t(const float* w, int cout, int cin, int ks, int row0, int nrows, int cout_pad_t, int cin_pad_t,
+                         void* packed, cudaStream_t s) {
+  if (cin_pad_t % kKC || cout_pad_t % 96 || nrows > cout_pad_t || cout > cin_pad_t || row0 + nrows > cin)
+    return fail(BIN_ERR_ARG, "pack_conv_weight_t: bad padding / row range");
+  const size_t total = (size_t)cout_pad_t * cin_pad_t * ks * ks;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, cout, cin, ks, cout_pad_t, cin_pad_t, 96, 0, 1, row0, nrows,
                                                           (__half*)packed);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
@@ -363,6 +644,67 @@ int launch_convlstm(const float* x, const float* c_prev, const float* h_prev, co
   convlstm_kernel<<<grid_for(total, 128), 128, 0, s>>>(x, c_prev, h_prev, w, b, h_out, c_out, B, H, W);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
+}
+int launch_p8_add(const bin_act_t& dst, int dplane0, const bin_act_t& src, int splane0, int nplanes, cudaStream_t s) {
+  const size_t hw = (size_t)dst.H * dst.W;
+  p8_add_kernel<<<grid_for((size_t)dst.B * nplanes * hw, 256), 256, 0, s>>>((__half*)dst.ptr, dst.planes, dplane0,
+      (const __half*)src.ptr, src.planes, splane0, nplanes, dst.B, hw);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_relu_mask(const bin_act_t& dg, int dplane0, const bin_act_t& g, int gplane0, int nplanes, cudaStream_t s) {
+  const size_t hw = (size_t)dg.H * dg.W;
+  p8_relu_mask_kernel<<<grid_for((size_t)dg.B * nplanes * hw, 256), 256, 0, s>>>((__half*)dg.ptr, dg.planes, dplane0,
+      (const __half*)g.ptr, g.planes, gplane0, nplanes, dg.B, hw);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_pixel_unshuffle(const bin_act_t& du, const bin_act_t& dst, cudaStream_t s) {
+  pixel_unshuffle_kernel<<<grid_for((size_t)dst.B * 32 * dst.H * dst.W, 256), 256, 0, s>>>((const __half*)du.ptr,
+      (__half*)dst.ptr, dst.B, dst.H, dst.W);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_unpack_frames_grad(const bin_act_t& dx0, const bin_frames_t& dout, const bin_frames_t& dfr, int H, int W,
+                              const float* scale, cudaStream_t s) {
+  const size_t total = (size_t)dx0.B * dfr.nframes * 3 * (H / 2) * (W / 2);
+  unpack_frames_grad_kernel<<<grid_for(total, 256), 256, 0, s>>>((const __half*)dx0.ptr, dx0.planes, dout, dfr, H, W, scale);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_grad_out_to_p8(const bin_frames_t& dout, int H, int W, const bin_act_t& dst, const float* scale, cudaStream_t s) {
+  grad_out_to_p8_kernel<<<grid_for((size_t)dst.B * 4 * H * W, 256), 256, 0, s>>>(dout, H, W, (__half*)dst.ptr, scale);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_bias_grad(const bin_act_t& dy, int plane0, int C, const float* scale, float* db, cudaStream_t s) {
+  const size_t hw = (size_t)dy.H * dy.W;
+  dim3 grid(64, (C + 7) / 8);
+  p8_bias_grad_kernel<<<grid, 256, 0, s>>>((const __half*)dy.ptr, dy.planes, plane0, C, dy.B, hw, scale, db);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_convlstm_bwd(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
+                        const float* dh, const float* dc, float* dgates_ws, float* dx, float* dc_prev, float* dh_prev,
+                        float* dw, float* db, int B, int H, int W, cudaStream_t s) {
+  if ((c_prev == nullptr) != (h_prev == nullptr)) return fail(BIN_ERR_ARG, "convlstm_bwd: give both c_prev and h_prev or neither");
+  const size_t total = (size_t)B * H * W;
+  convlstm_bwd_gates_kernel<<<grid_for(total, 128), 128, 0, s>>>(x, c_prev, h_prev, w, b, dh, dc, dgates_ws, dc_prev, B, H, W);
+  BIN_CUDA_OK(cudaGetLastError());
+  const int chunk = 2048;
+  convlstm_bwd_weights_kernel<<<(unsigned)((total + chunk - 1) / chunk), 256, 0, s>>>(x, h_prev, dgates_ws, dw, db, B, H, W, chunk);
+  BIN_CUDA_OK(cudaGetLastError());
+  convlstm_bwd_input_kernel<<<grid_for(total, 128), 128, 0, s>>>(dgates_ws, w, dx, dh_prev, B, H, W);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_wgrad_impl(const bin_act_t& x0, int x0_plane0, int x0_planes, const bin_act_t& x1, int x1_plane0, int x1_planes,
+                      const bin_act_t& dy, int dy_plane0, int cout, int cin, int ks, const float* scale, float* dw,
+                      cudaStream_t s);
+int launch_wgrad(const bin_act_t& x0, int x0_plane0, int x0_planes, const bin_act_t& x1, int x1_plane0, int x1_planes,
+                 const bin_act_t& dy, int dy_plane0, int cout, int cin, int ks, const float* scale, float* dw,
+                 cudaStream_t s) {
+  return launch_wgrad_impl(x0, x0_plane0, x0_planes, x1, x1_plane0, x1_planes, dy, dy_plane0, cout, cin, ks, scale, dw, s);
 }
 int run_mma_bench(int n, int iters, int mode, float* cycles_host) {
   if (n < 16 || n > 256 || n % 16) return fail(BIN_ERR_ARG, "microbench: N must be a multiple of 16 in [16,256]");

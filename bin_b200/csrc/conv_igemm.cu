@@ -136,7 +136,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     ctrl->issued = 0;
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < NT * p.nh; i += blockDim.x) sbias[i] = p.bias[i];
+  const bool bias_in_smem = NT * p.nh <= 256;                  // else (wide data-gradient launches) read it from global
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < NT * p.nh; i += blockDim.x) sbias[i] = p.bias[i];
+  const float* bsrc = bias_in_smem ? sbias : p.bias;
   if (warp == 2) {
     tmem_alloc(&ctrl->tmem_base, C::TMEM_COLS);
     tmem_relinquish();
@@ -283,7 +286,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 #pragma unroll
           for (int k = 0; k < NT / 8; ++k) {
             const size_t off = ((((size_t)b * p.res_planes + p.res_plane0 + (nh * NT) / 8 + k) * p.H + y) * p.W + x) * 8;
-            rbuf[k] = valid ? *reinterpret_cast<const uint4*>(p.res + off) : make_uint4(0, 0, 0, 0);
+            rbuf[k] = (valid && (nh * NT) / 8 + k < p.store_planes) ? *reinterpret_cast<const uint4*>(p.res + off)
+                                                                   : make_uint4(0, 0, 0, 0);
           }
         }
       }
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             tmem_ld16(taddr + n0, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + sbias[nh * NT + n0 + i];
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bsrc[nh * NT + n0 + i];
           }
           if (valid) {
             if (p.relu) {
@@ -359,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
               o.z = pack_h2(f[h * 8 + 4], f[h * 8 + 5]);
               o.w = pack_h2(f[h * 8 + 6], f[h * 8 + 7]);
               const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + cpl + h) * p.H + y) * p.W + x) * 8;
-              *reinterpret_cast<uint4*>(p.out + off) = o;
+              if (cpl + h < p.store_planes) *reinterpret_cast<uint4*>(p.out + off) = o;
             }
           }
         }
@@ -476,6 +480,22 @@ int make_p8_tmap(CUtensorMap* m, const bin_act_t& t, int box_rows) {
 
 long long* g_dbg = nullptr;   // perf-debug timeline buffer (tools only)
 
+// Generic P8 box: box_px pixels x box_rows rows x box_planes planes (used by the weight-gradient kernel).
+int make_p8_tmap_box(CUtensorMap* m, const bin_act_t& t, int box_px, int box_rows, int box_planes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(BIN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(t.ptr) & 15) != 0) return fail(BIN_ERR_ARG, "P8 tensor not 16-byte aligned");
+  if (box_px * 8 > 256 || box_rows > 256 || box_planes > 256) return fail(BIN_ERR_ARG, "TMA box dimension exceeds 256");
+  cuuint64_t dims[4] = {(cuuint64_t)t.W * 8, (cuuint64_t)t.H, (cuuint64_t)t.planes, (cuuint64_t)t.B};
+  cuuint64_t strides[3] = {(cuuint64_t)t.W * 16, (cuuint64_t)t.H * t.W * 16, (cuuint64_t)t.planes * t.H * t.W * 16};
+  cuuint32_t box[4] = {(cuuint32_t)box_px * 8, (cuuint32_t)box_rows, (cuuint32_t)box_planes, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, t.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BIN_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return BIN_OK;
+}
+
 static int num_sms() {
   static int n = []() {
     int dev = 0, v = 0;
@@ -534,6 +554,7 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
   p.cps = cps;
   const int smem_bytes = kCtrlBytes + res_bytes + S * cps * unit_bytes + 256;
   p.out = reinterpret_cast<__half*>(a.out.ptr); p.out_planes = a.out.planes; p.out_plane0 = a.out_plane0;
+  p.store_planes = a.store_planes > 0 ? a.store_planes : a.cout_pad / 8;
   p.res = reinterpret_cast<const __half*>(a.res.ptr); p.res_planes = a.res.planes; p.res_plane0 = a.res_plane0;
   p.fr = a.fr;
   { const char* e = getenv("BIN_B200_DEBUG"); p.debug = (e && *e) ? atoi(e) : 0; }   // perf experiments only
@@ -571,17 +592,18 @@ int launch_conv(const bin_conv_args_t& a, cudaStream_t s) {
   if (a.in0_plane0 + a.in0_planes > a.in0.planes || (a.in1_planes > 0 && a.in1_plane0 + a.in1_planes > a.in1.planes))
     return fail(BIN_ERR_ARG, "input plane range exceeds tensor");
   if (a.epilogue == BIN_EPI_P8) {
-    if (a.out.H != a.in0.H || a.out.W != a.in0.W || a.out.B != a.in0.B ||
-        a.out_plane0 + a.cout_pad / 8 > a.out.planes)
+    const int nstore = a.store_planes > 0 ? a.store_planes : a.cout_pad / 8;
+    if (a.out.H != a.in0.H || a.out.W != a.in0.W || a.out.B != a.in0.B || nstore > a.cout_pad / 8 ||
+        a.out_plane0 + nstore > a.out.planes)
       return fail(BIN_ERR_ARG, "output tensor geometry mismatch");
     if (a.res.ptr && (a.res.H != a.in0.H || a.res.W != a.in0.W || a.res.B != a.in0.B ||
-                      a.res_plane0 + a.cout_pad / 8 > a.res.planes))
+                      a.res_plane0 + nstore > a.res.planes))
       return fail(BIN_ERR_ARG, "residual tensor geometry mismatch");
     if (a.ksize == 3 && a.cout_pad == 32 && a.variant == 0) return launch_inst<32, 3, BIN_EPI_P8, true>(a, s);
     if (a.ksize == 3 && a.cout_pad == 32 && a.variant == 1) return launch_inst<32, 3, BIN_EPI_P8, false>(a, s);
-    if (a.ksize == 3 && a.cout_pad == 96) return launch_inst<96, 3, BIN_EPI_P8, false>(a, s);
+    if (a.ksize == 3 && a.cout_pad % 96 == 0) return launch_inst<96, 3, BIN_EPI_P8, false>(a, s);
     if (a.ksize == 5 && a.cout_pad == 96) return launch_inst<96, 5, BIN_EPI_P8, false>(a, s);
-    if (a.ksize == 1 && a.cout_pad == 96) return launch_inst<96, 1, BIN_EPI_P8, false>(a, s);
+    if (a.ksize == 1 && a.cout_pad % 96 == 0) return launch_inst<96, 1, BIN_EPI_P8, false>(a, s);
   } else if (a.epilogue == BIN_EPI_PIXSHUF) {
     if (a.out.H != 2 * a.in0.H || a.out.W != 2 * a.in0.W || a.out.B != a.in0.B ||
         a.out_plane0 + a.cout_pad / 32 > a.out.planes)

@@ -45,7 +45,7 @@ struct alignas(64) ConvParams {
   int b0, y0, ny;                      // batch / row sub-range processed by this launch
   int tiles_x, tiles_y, ntiles, nh;    // nh = cout_pad / NT
   int relu, resident, nstages, cps, debug;
-  __half* out; int out_planes, out_plane0;
+  __half* out; int out_planes, out_plane0, store_planes;
   const __half* res; int res_planes, res_plane0;
   bin_frames_t fr;
   long long* dbg;
@@ -55,6 +55,6 @@ extern long long* g_dbg;
 int launch_conv(const bin_conv_args_t& a, cudaStream_t s);
 
 // packed-weight geometry
-inline int conv_nt(int cout_pad) { return cout_pad > 128 ? 128 : cout_pad; }
+inline int conv_nt(int cout_pad) { return cout_pad % 96 == 0 ? 96 : (cout_pad > 128 ? 128 : cout_pad); }
 
 }  // namespace binb

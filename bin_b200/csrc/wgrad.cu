@@ -1,0 +1,215 @@
+// bin_b200 -- weight-gradient GEMM for sm_100a (tcgen05.mma with MN-major operands).
+//
+// dW[co][ci][ky][kx] += (1/scale) * sum_{b,y,x} dY[b,co,y,x] * X[b,ci,y+ky-pad,x+kx-pad]
+// (the wgrad of every nn.Conv2d of RDN.py; autograd of bin_model.optimize_parameters, bin_model.py:130-141).
+//
+// GEMM view: D_tap[ci][co] = sum_pixels X_tap[pixel][ci] * dY[pixel][co], i.e. M = Cin tile (128),
+// N = Cout, K = pixels.  P8 tiles in shared memory ([plane][row][px][8 ch]) are exactly the canonical
+// MN-major / no-swizzle UMMA layout with K = pixel index: 8 channels contiguous (16 B), 8 consecutive
+// pixels 16 B apart (one 128-byte core matrix), next 8-pixel group +128 B (LBO), next 8-channel plane
+// +plane stride (SBO).  A tap is again a 16-byte start-address shift of the X halo tile.
+// One MMA = 128(ci) x N(co) x 16 pixels (one 16-pixel tile row); a CTA keeps one fp32 accumulator per
+// tap in TMEM (taps x Cout <= 512 columns; wider layers run several tap groups), walks a slice of the
+// pixel tiles, and finally adds its partial sums into dW with fp32 atomics.
+#include <stdio.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace binb {
+
+constexpr int kWgTW = 16, kWgTH = 8;      // pixel tile: 8 rows x 16 px (K = 16 px per MMA)
+
+struct alignas(64) WgradParams {
+  CUtensorMap xmap0, xmap1, ymap;
+  int x0_plane0, x0_planes, x1_plane0, x1_planes;   // Cin segments (planes of 8 channels)
+  int ci_tile_plane0;                               // first logical input plane of this launch's 128-channel tile
+  int dy_plane0, n;                                 // N = cout padded to 16
+  int ks, pad, pw, rows;                            // X tile pitch (px) and rows incl. halo
+  int tap0, ntaps;                                  // tap group handled by this launch
+  int cout, cin;                                    // real sizes (flush bounds)
+  int B, H, W, tiles_x, tiles_y, ntiles;
+  int nstages;
+  const float* scale;
+  float* dw;
+};
+
+struct WgCtrl {
+  uint64_t full[4], empty[4], done;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;    // stride between 8-element K groups (8 pixels)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;    // stride between 8-element MN groups (channel planes)
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  WgCtrl* ctrl = reinterpret_cast<WgCtrl*>(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x_plane_bytes = p.rows * p.pw * 16;
+  const int x_bytes = 16 * x_plane_bytes;                       // 16 planes = 128 input channels
+  const int y_planes = p.n / 8;
+  const int y_plane_bytes = kWgTH * kWgTW * 16;
+  const int y_bytes = y_planes * y_plane_bytes;
+  const int stage_bytes = x_bytes + y_bytes;
+  uint8_t* stage0 = smem + 1024;
+  const uint32_t S = p.nstages;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.xmap0);
+    if (p.x1_planes > 0) tma_prefetch_desc(&p.xmap1);
+    tma_prefetch_desc(&p.ymap);
+    for (int i = 0; i < 4; ++i) { mbar_init(&ctrl->full[i], 1); mbar_init(&ctrl->empty[i], 1); }
+    mbar_init(&ctrl->done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(&ctrl->tmem_base, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------ TMA producer
+    uint32_t s = 0, ph = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      int t = tile;
+      const int txi = t % p.tiles_x; t /= p.tiles_x;
+      const int tyi = t % p.tiles_y;
+      const int b = t / p.tiles_y;
+      mbar_wait(&ctrl->empty[s], ph ^ 1);
+      uint8_t* dst = stage0 + (size_t)s * stage_bytes;
+      // the X tile is assembled from 4-plane boxes; planes past the conv's Cin are zero-filled by hand-off
+      // to TMA's out-of-bounds fill (coordinates beyond the tensor) or skipped (rows ignored at the flush)
+      int nbox = 0;
+      for (int q = 0; q < 4; ++q) {
+        const int lp = p.ci_tile_plane0 + 4 * q;               // logical input plane
+        if (lp < p.x0_planes + p.x1_planes) ++nbox;
+      }
+      mbar_expect_tx(&ctrl->full[s], (uint32_t)(nbox * 4 * x_plane_bytes + y_bytes));
+      for (int q = 0; q < 4; ++q) {
+        const int lp = p.ci_tile_plane0 + 4 * q;
+        if (lp >= p.x0_planes + p.x1_planes) continue;
+        const bool seg1 = lp >= p.x0_planes;
+        const void* tmap = seg1 ? (const void*)&p.xmap1 : (const void*)&p.xmap0;
+        const int plane = seg1 ? p.x1_plane0 + (lp - p.x0_planes) : p.x0_plane0 + lp;
+        tma_load_4d(dst + (size_t)q * 4 * x_plane_bytes, tmap, &ctrl->full[s], (txi * kWgTW - p.pad) * 8,
+                    tyi * kWgTH - p.pad, plane, b);
+      }
+      tma_load_4d(dst + x_bytes, &p.ymap, &ctrl->full[s], txi * kWgTW * 8, tyi * kWgTH, p.dy_plane0, b);
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer: D_tap[ci][co] += X_tap^T * dY
+    const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t s = 0, ph = 0;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      mbar_wait(&ctrl->full[s], ph);
+      tc_fence_after();
+      const uint32_t xb = smem_u32(stage0 + (size_t)s * stage_bytes);
+      const uint32_t yb = xb + x_bytes;
+      if (elect_one()) {
+        for (int tp = 0; tp < p.ntaps; ++tp) {
+          const int tap = p.tap0 + tp, ky = tap / p.ks, kx = tap % p.ks;
+          const uint32_t d = tmem_base + tp * p.n;
+          for (int r = 0; r < kWgTH; ++r) {
+            const uint64_t ad = umma_desc_mnmajor_noswz(xb + (uint32_t)((r + ky) * p.pw + kx) * 16, 128, x_plane_bytes);
+            const uint64_t bd = umma_desc_mnmajor_noswz(yb + (uint32_t)(r * kWgTW) * 16, 128, y_plane_bytes);
+            umma_f16_ss(d, ad, bd, idesc, (first && r == 0) ? 0u : 1u);
+          }
+        }
+        umma_commit(&ctrl->empty[s]);
+      }
+      __syncwarp();
+      first = false;
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+    if (elect_one()) umma_commit(&ctrl->done);
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------ flush: TMEM -> fp32 atomics into dW (OIHW)
+    mbar_wait(&ctrl->done, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int ci = p.ci_tile_plane0 * 8 + q * 32 + lane;        // this thread's input channel (accumulator row)
+    const float inv = 1.f / p.scale[0];
+    const int kk = p.ks * p.ks;
+    const bool has_tiles = (int)blockIdx.x < p.ntiles;
+    for (int tp = 0; tp < p.ntaps; ++tp) {
+      for (int n0 = 0; n0 < p.n; n0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tp * p.n + n0, v);
+        tmem_ld_wait();
+        if (has_tiles && ci < p.cin) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int co = n0 + i;
+            if (co < p.cout) atomicAdd(p.dw + ((size_t)co * p.cin + ci) * kk + p.tap0 + tp, __uint_as_float(v[i]) * inv);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+int make_p8_tmap_box(CUtensorMap* m, const bin_act_t& t, int box_px, int box_rows, int box_planes);
+
+int launch_wgrad_impl(const bin_act_t& x0, int x0_plane0, int x0_planes, const bin_act_t& x1, int x1_plane0, int x1_planes,
+                      const bin_act_t& dy, int dy_plane0, int cout, int cin, int ks, const float* scale, float* dw,
+                      cudaStream_t s) {
+  if (ks != 1 && ks != 3 && ks != 5) return fail(BIN_ERR_ARG, "wgrad: ksize must be 1, 3 or 5");
+  const int n = (cout + 15) / 16 * 16;
+  if (n > 256) return fail(BIN_ERR_UNSUPPORTED, "wgrad: Cout > 256");
+  if (dy_plane0 + n / 8 > dy.planes) return fail(BIN_ERR_ARG, "wgrad: dY plane range exceeds tensor");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.pad = ks / 2; p.ks = ks;
+  p.pw = kWgTW + 2 * p.pad; p.rows = kWgTH + 2 * p.pad;
+  BIN_TRY(make_p8_tmap_box(&p.xmap0, x0, p.pw, p.rows, 4));
+  if (x1_planes > 0) BIN_TRY(make_p8_tmap_box(&p.xmap1, x1, p.pw, p.rows, 4));
+  BIN_TRY(make_p8_tmap_box(&p.ymap, dy, kWgTW, kWgTH, n / 8));
+  p.x0_plane0 = x0_plane0; p.x0_planes = x0_planes; p.x1_plane0 = x1_plane0; p.x1_planes = x1_planes;
+  p.dy_plane0 = dy_plane0; p.n = n; p.cout = cout; p.cin = cin;
+  p.B = x0.B; p.H = x0.H; p.W = x0.W;
+  p.tiles_x = (p.W + kWgTW - 1) / kWgTW; p.tiles_y = (p.H + kWgTH - 1) / kWgTH;
+  p.ntiles = p.B * p.tiles_x * p.tiles_y;
+  p.scale = scale; p.dw = dw;
+  const int x_bytes = 16 * p.rows * p.pw * 16, y_bytes = (n / 8) * kWgTH * kWgTW * 16;
+  int S = (kSmemMax - 1024) / (x_bytes + y_bytes);
+  if (S > 3) S = 3;
+  if (S < 1) return fail(BIN_ERR_UNSUPPORTED, "wgrad: tile does not fit in shared memory");
+  p.nstages = S;
+  const int smem_bytes = 1024 + S * (x_bytes + y_bytes);
+  static bool attr_done = false;
+  if (!attr_done) {
+    BIN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    attr_done = true;
+  }
+  const int kk = ks * ks;
+  const int taps_per_group = 512 / n < kk ? 512 / n : kk;
+  const int ci_planes = x0_planes + x1_planes;
+  int grid = p.ntiles < 148 ? p.ntiles : 148;
+  if (grid < 1) return BIN_OK;
+  for (int cp = 0; cp < ci_planes; cp += 16) {
+    for (int t0 = 0; t0 < kk; t0 += taps_per_group) {
+      p.ci_tile_plane0 = cp;
+      p.tap0 = t0;
+      p.ntaps = kk - t0 < taps_per_group ? kk - t0 : taps_per_group;
+      wgrad_kernel<<<grid, 256, smem_bytes, s>>>(p);
+      BIN_CUDA_OK(cudaGetLastError());
+    }
+  }
+  return BIN_OK;
+}
+
+}  // namespace binb

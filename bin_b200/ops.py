@@ -100,7 +100,7 @@ def conv_fwd(in0: torch.Tensor, w_packed: torch.Tensor, bias_pad: torch.Tensor, 
              relu: bool = False, epilogue: int = _lib.EPI_P8,
              out: Optional[torch.Tensor] = None, out_plane0: int = 0,
              res: Optional[torch.Tensor] = None, res_plane0: int = 0,
-             frames: Optional[Frames] = None, variant: int = 0, sub=None) -> None:
+             frames: Optional[Frames] = None, variant: int = 0, sub=None, store_planes: int = 0) -> None:
     a = ConvArgs()
     a.in0 = act_view(in0)
     a.in0_plane0 = in0_plane0
@@ -121,6 +121,7 @@ def conv_fwd(in0: torch.Tensor, w_packed: torch.Tensor, bias_pad: torch.Tensor, 
         a.fr = frames
     if sub is not None:
         a.b_begin, a.b_count, a.y_begin, a.y_count = sub
+    a.store_planes = store_planes
     check(lib().bin_conv_fwd(C.byref(a), _stream()))
 
 

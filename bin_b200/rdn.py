@@ -261,6 +261,10 @@ class RDN_residual_interp_5_input(nn.Module):
     def forward(self, B1, B3, B5, B7, B9, previous_input=None):
         """10 backbone calls of RDN.py:367-405, issued as 4 batched launches (same-weight calls
         ride along the batch dimension)."""
+        if torch.is_grad_enabled() and (any(t.requires_grad for t in (B1, B3, B5, B7, B9)) or
+                                        self.model1_1.SFENet1.weight.requires_grad):
+            from .autograd import pyramid_apply
+            return pyramid_apply(self, B1, B3, B5, B7, B9, previous_input)
         m1, m2, m3, m4 = self.model1_1, self.model2_1, self.model3_1, self.model4_1
         I2, I4, I6, I8 = _batched(m1, [(B1, B3), (B3, B5), (B5, B7), (B7, B9)])
         if previous_input is not None and previous_input[0] is not None:
@@ -276,8 +280,6 @@ class RDN_residual_interp_5_input(nn.Module):
 
 
 def _batched(model: _Backbone, calls):
-    if torch.is_grad_enabled() and (any(t.requires_grad for c in calls for t in c) or model.SFENet1.weight.requires_grad):
-        return [model(*c) for c in calls]
     calls = [[t.contiguous() for t in c] for c in calls]
     B, H, W = _check_frames([t for c in calls for t in c])
     dev = calls[0][0].device

@@ -86,7 +86,7 @@ typedef struct {
   bin_act_t in1; int in1_plane0, in1_planes; /* in1_planes = 0 -> unused */
   const void* w_packed; const float* bias;   /* bias: fp32[cout_pad] */
   int ksize;     /* 1, 3 or 5; stride 1, zero padding ksize/2 (all convs of RDN.py) */
-  int cout_pad;  /* 16, 32, 96 or 256 */
+  int cout_pad;  /* 16, 32, 256 or a multiple of 96 */
   int relu;      /* RDN.py:142 */
   int epilogue;  /* BIN_EPI_* */
   int variant;   /* BIN_CONV_*; must match the variant the weights were packed with */
@@ -94,6 +94,9 @@ typedef struct {
    * [y_begin, y_begin+y_count); counts of 0 mean "to the end".  Used to walk an RDB band by band
    * so that its intermediate tensors stay L2-resident. */
   int b_begin, b_count, y_begin, y_count;
+  /* BIN_EPI_P8 only: number of output planes actually stored (0 = cout_pad/8); lets a conv whose Cout was
+   * zero-padded up to a multiple of 96 (the data-gradient launches) write a narrower tensor. */
+  int store_planes;
   /* BIN_EPI_P8: out planes [out_plane0, +cout_pad/8), optional residual (RDN.py:165, :219) */
   bin_act_t out; int out_plane0;
   bin_act_t res; int res_plane0; /* res.ptr = NULL -> none */
@@ -104,11 +107,27 @@ typedef struct {
 } bin_conv_args_t;
 int bin_conv_fwd(const bin_conv_args_t* a, bin_stream_t s);
 
+/* Data-gradient weights of a conv (cout,cin,k): V[ci][co][ky][kx] = W[co][row0+ci][k-1-ky][k-1-kx] for ci < nrows,
+ * packed like a forward conv with Cout' = cout_pad_t (multiple of 96), Cin' = cin_pad_t (multiple of 32):
+ * bin_conv_fwd over dY with these weights gives dX[:, row0:row0+nrows]. */
+int bin_pack_conv_weight_t(const float* w_oihw, int cout, int cin, int ksize, int row0, int nrows, int cout_pad_t,
+                           int cin_pad_t, void* packed, bin_stream_t s);
+/* Weight gradient of one conv: dw (cout,cin,k,k fp32 OIHW) += (1/ *scale_dev) * sum_px dY[px][co] X[px+tap][ci];
+ * X = planes of x0 followed by planes of x1 (like bin_conv_args_t), dY = planes [dy_plane0, +ceil(cout/8)). */
+int bin_conv_wgrad(bin_act_t x0, int x0_plane0, int x0_planes, bin_act_t x1, int x1_plane0, int x1_planes, bin_act_t dy,
+                   int dy_plane0, int cout, int cin, int ksize, const float* scale_dev, float* dw, bin_stream_t s);
+
 /* ---- ConvLSTMCell.forward, RDN.py:50-95 ------------------------------------------------ */
 /* x,(c_prev,h_prev): (B,3,H,W) fp32; c_prev/h_prev NULL = zeros (RDN.py:57-68);
  * w: (12,6,3,3), b: (12); writes h_out and (optionally) c_out. */
 int bin_convlstm_fwd(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
                      float* h_out, float* c_out, int B, int H, int W, bin_stream_t s);
+
+/* Backward of the cell: dh/dc = gradients of the two outputs (either may be NULL = zero); dgates_ws = scratch
+ * (B,12,H,W) fp32; writes dx (and dc_prev/dh_prev when a state was given), ACCUMULATES into dw (12,6,3,3) and db (12). */
+int bin_convlstm_bwd(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
+                     const float* dh, const float* dc, float* dgates_ws, float* dx, float* dc_prev, float* dh_prev,
+                     float* dw, float* db, int B, int H, int W, bin_stream_t s);
 
 /* ---- one backbone (RDN_residual_interp_{2,2_1,4_1}_input.forward, RDN.py:210-334) ---------- */
 #define BIN_BACKBONE_NCONV 66 /* SFENet1, SFENet2, 12 x (4 conv + LFF), GFF.0, GFF.1, UPNet.0, UPNet.2 */
@@ -119,6 +138,23 @@ int bin_backbone_pack(int nframes, const float* const* w_host, const float* cons
 size_t bin_backbone_workspace_bytes(int nframes, int Btot, int H, int W);
 int bin_backbone_fwd(int nframes, const void* blob, const bin_frames_t* fr, int H, int W, void* workspace,
                      size_t workspace_bytes, bin_stream_t s);
+/* ---- training: forward that keeps the activations + backward (bin_model.optimize_parameters,
+ * bin_model.py:130-141 -> l_pix.backward()).  Gradients flow as loss-scaled fp16 P8 tensors:
+ * *scale_dev (device float, a power of two chosen by the caller from max|dOut|) multiplies dOut on entry
+ * and is divided out of every result (frame gradients, dW, db). */
+size_t bin_backbone_packed_t_bytes(int nframes);             /* data-gradient (transposed, tap-flipped) weights */
+int bin_backbone_pack_t(int nframes, const float* const* w_host, void* blob_t, bin_stream_t s);
+size_t bin_backbone_train_workspace_bytes(int nframes, int Btot, int H, int W);   /* saved activations */
+int bin_backbone_fwd_train(int nframes, const void* blob, const bin_frames_t* fr, int H, int W, void* save_ws,
+                           size_t save_ws_bytes, bin_stream_t s);
+size_t bin_backbone_grad_workspace_bytes(int nframes, int Btot, int H, int W);
+size_t bin_backbone_grad_param_floats(int nframes);          /* fp32 [w0,b0,w1,b1,...] in nn.Module order */
+/* dout->out[k]: dL/d(output of call k), (Bc,3,H,W) fp32.  dframes->frame[k][f]: receives dL/d(frame f of call k)
+ * (written, not accumulated; the caller sums frames that feed several calls).  grad_params is ACCUMULATED into. */
+int bin_backbone_bwd(int nframes, const void* blob_t, const bin_frames_t* dout, const bin_frames_t* dframes, int H, int W,
+                     const void* save_ws, void* grad_ws, size_t grad_ws_bytes, float* grad_params,
+                     const float* scale_dev, bin_stream_t s);
+
 /* Unit-test entry: one RDB (RDN.py:149-165) on fp32 NCHW (B,96,h,w), using RDB `index` of the blob. */
 int bin_rdb_fwd(const void* blob, int nframes, int index, const float* x, float* y, int B, int h, int w,
                 void* workspace, size_t workspace_bytes, bin_stream_t s);

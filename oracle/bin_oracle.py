@@ -122,8 +122,31 @@ def space_to_depth2(x: Tensor) -> Tensor:
     return v.reshape(B, Cc * 4, H // 2, W // 2)
 
 
+_EMULATE_FP16 = False      # tests only: round weights / stored activations to fp16 like the CUDA path stores them
+
+
+class emulate_fp16_storage:
+    """Context manager: the oracle rounds conv weights and every tensor the CUDA path stores in fp16
+    (packed input, each conv's stored output) to fp16 precision (straight-through for autograd).  Used by the
+    backward tests to separate kernel errors from ReLU sign flips caused by fp16-vs-fp32 forward differences."""
+
+    def __enter__(self):
+        global _EMULATE_FP16
+        self.prev, _EMULATE_FP16 = _EMULATE_FP16, True
+
+    def __exit__(self, *a):
+        global _EMULATE_FP16
+        _EMULATE_FP16 = self.prev
+
+
+def _q(t: Tensor) -> Tensor:
+    if not _EMULATE_FP16:
+        return t
+    return t + (t.half().float() - t).detach()
+
+
 def conv(x: Tensor, sd: SD, name: str) -> Tensor:
-    w = sd[name + ".weight"]
+    w = _q(sd[name + ".weight"])
     return F.conv2d(x, w, sd[name + ".bias"], stride=1, padding=w.shape[-1] // 2)
 
 
@@ -131,22 +154,22 @@ def rdb(x: Tensor, sd: SD, prefix: str) -> Tensor:
     """RDN.py:135-165: 4 x (conv3x3 -> ReLU -> concat) -> LFF 1x1 -> + x."""
     feat = x
     for c in range(C):
-        g = F.relu(conv(feat, sd, f"{prefix}.convs.{c}.conv.0"))          # :140-146
+        g = _q(F.relu(conv(feat, sd, f"{prefix}.convs.{c}.conv.0")))      # :140-146
         feat = torch.cat((feat, g), 1)                                     # :147
-    return conv(feat, sd, f"{prefix}.LFF") + x                             # :165
+    return _q(conv(feat, sd, f"{prefix}.LFF") + x)                         # :165
 
 
 def backbone(frames: Sequence[Tensor], sd: SD, return_feats: bool = False):
     """RDN.py:210-222 / 268-280 / 322-334 (identical up to the frame count)."""
-    x0 = space_to_depth2(torch.cat(list(frames), 1))                       # :211
-    f1 = conv(x0, sd, "SFENet1")                                           # :212
-    x = conv(f1, sd, "SFENet2")                                            # :213
+    x0 = _q(space_to_depth2(torch.cat(list(frames), 1)))                   # :211
+    f1 = _q(conv(x0, sd, "SFENet1"))                                       # :212
+    x = _q(conv(f1, sd, "SFENet2"))                                        # :213
     outs = []
     for i in range(D):                                                     # :215-217
         x = rdb(x, sd, f"RDBs.{i}")
         outs.append(x)
-    x = conv(conv(torch.cat(outs, 1), sd, "GFF.0"), sd, "GFF.1") + f1      # :218-219
-    up = F.pixel_shuffle(conv(x, sd, "UPNet.0"), 2)                        # :205-206
+    x = _q(conv(_q(conv(torch.cat(outs, 1), sd, "GFF.0")), sd, "GFF.1") + f1)   # :218-219
+    up = _q(F.pixel_shuffle(conv(x, sd, "UPNet.0"), 2))                    # :205-206
     y = conv(up, sd, "UPNet.2")                                            # :207
     mean = sum(frames) / float(len(frames))                                # :221 / :279 / :333
     out = y + mean

@@ -53,7 +53,8 @@ def test_cpu_forward_fails_loudly(net):
         net(*fr)
 
 
-def test_grad_path_fails_loudly(net):
+def test_grad_path_on_cpu_fails_loudly(net):
+    """Training goes through the same CUDA library: a grad-enabled CPU call must raise, not fall back."""
     from bin_b200 import BinB200Error
     fr = O.synth_frames(6, 1, 16, 16)
     with pytest.raises(BinB200Error):
