@@ -106,6 +106,32 @@ def cpu_oracle_sample(sample_hw=(128, 128), threads=None, reps=1):
     return dt, threads
 
 
+def run_reference_cuda(args):
+    """Context number for BASELINE.md: the oracle port (same PyTorch ops as the reference) run eagerly on the
+    SAME B200 through cuDNN, fp32 and fp16-autocast -- the bar a PyTorch user sees today."""
+    import torch
+    from oracle import bin_oracle as O
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = True                      # as test.py:148
+    H, W = args.height, args.width
+    sd = {k: v.to(dev) for k, v in O.synth_state_dict(0).items()}
+    fr = [f.to(dev) for f in O.synth_frames(6, 1, H, W, seed=1234, smooth=True)]
+    res = {}
+    for tag, ctx in (("fp32", torch.autocast("cuda", enabled=False)), ("fp16_autocast", torch.autocast("cuda", dtype=torch.float16))):
+        with torch.no_grad(), ctx:
+            for _ in range(max(2, args.warmup)):
+                O.window_forward(fr, sd)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                O.window_forward(fr, sd)
+            e1.record()
+            torch.cuda.synchronize()
+        res[tag] = {"ms_per_window": e0.elapsed_time(e1) / args.steps, "windows_per_s": args.steps / (e0.elapsed_time(e1) * 1e-3)}
+    print(json.dumps({"impl": "reference-port-eager-cuda", "metric": METRIC, "unit": UNIT, "config": {"workload": f"bin_stage4 6-frame window {W}x{H}", "calls": "all 20 backbone calls as the reference executes them", "tf32": bool(torch.backends.cudnn.allow_tf32)}, **res}), flush=True)
+
+
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the path.  /root/reference is a
     Python repo that is not present on the GPU box, so this leg times oracle/bin_oracle.py -- the
@@ -287,11 +313,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--height", type=int, default=720)
     ap.add_argument("--width", type=int, default=1280)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl == "reference-cuda":
+        run_reference_cuda(args)
+    elif args.impl == "reference":
         run_reference(args)                     # each step is a bounded ~4 s sample (192x256 window)
     else:
         args.warmup = max(args.warmup, 3)
