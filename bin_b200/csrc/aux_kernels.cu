@@ -364,35 +364,53 @@ __global__ void convlstm_bwd_gates_kernel(const float* __restrict__ x, const flo
   }
 }
 // Pass 2: dW[k][c][tap] += sum_p dgates[k][p] * in[c][p+off], db[k] += sum_p dgates[k][p]  (660 outputs).
-__global__ void convlstm_bwd_weights_kernel(const float* __restrict__ x, const float* __restrict__ h_prev,
-                                            const float* __restrict__ dgates, float* __restrict__ dw,
-                                            float* __restrict__ db, int B, int H, int W, int chunk) {
+// 9 warps per block, warp v owns tap v: 72 register accumulators acc[k][c] (all indices compile-time), lanes
+// stride over pixels; one warp-shuffle reduction + 72 atomics per warp at the end (warp 0 also sums the biases).
+__global__ void __launch_bounds__(288) convlstm_bwd_weights_kernel(const float* __restrict__ x, const float* __restrict__ h_prev,
+                                                                    const float* __restrict__ dgates, float* __restrict__ dw,
+                                                                    float* __restrict__ db, int B, int H, int W) {
   const size_t hw = (size_t)H * W;
   const size_t total = (size_t)B * hw;
-  const size_t p0 = (size_t)blockIdx.x * chunk;
-  const size_t p1 = p0 + chunk < total ? p0 + chunk : total;
-  for (int o = threadIdx.x; o < 660; o += blockDim.x) {
-    float acc = 0.f;
-    if (o < 648) {
-      const int k = o / 54, c = (o / 9) % 6, tap = o % 9, ky = tap / 3 - 1, kx = tap % 3 - 1;
-      if (c < 3 || h_prev) {
-        const float* src = c < 3 ? x : h_prev;
-        const int cc = c < 3 ? c : c - 3;
-        for (size_t p = p0; p < p1; ++p) {
-          const int xw = p % W, y = (p / W) % H, b = p / hw;
-          const int yy = y + ky, xx = xw + kx;
-          if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-          acc = fmaf(dgates[((size_t)b * 12 + k) * hw + (size_t)y * W + xw], src[((size_t)b * 3 + cc) * hw + (size_t)yy * W + xx], acc);
-        }
-      }
-      atomicAdd(dw + o, acc);
-    } else {
-      const int k = o - 648;
-      for (size_t p = p0; p < p1; ++p) {
-        const int b = p / hw;
-        acc += dgates[((size_t)b * 12 + k) * hw + (p % hw)];
-      }
-      atomicAdd(db + k, acc);
+  const int tap = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+  float acc[12][6];
+  float accb[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    accb[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[k][c] = 0.f;
+  }
+  for (size_t p = (size_t)blockIdx.x * 32 + lane; p < total; p += (size_t)gridDim.x * 32) {
+    const int xw = p % W, y = (p / W) % H, b = p / hw;
+    const int yy = y + dy, xx = xw + dx;
+    const bool inb = yy >= 0 && yy < H && xx >= 0 && xx < W;
+    float in[6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      in[c] = inb ? x[((size_t)b * 3 + c) * hw + (size_t)yy * W + xx] : 0.f;
+      in[3 + c] = (inb && h_prev) ? h_prev[((size_t)b * 3 + c) * hw + (size_t)yy * W + xx] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const float d = dgates[((size_t)b * 12 + k) * hw + (size_t)y * W + xw];
+      accb[k] += d;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[k][c] = fmaf(d, in[c], acc[k][c]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      float v = acc[k][c];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) atomicAdd(dw + (k * 6 + c) * 9 + tap, v);
+    }
+    if (tap == 0) {
+      float v = accb[k];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) atomicAdd(db + k, v);
     }
   }
 }
@@ -691,8 +709,8 @@ int launch_convlstm_bwd(const float* x, const float* c_prev, const float* h_prev
   const size_t total = (size_t)B * H * W;
   convlstm_bwd_gates_kernel<<<grid_for(total, 128), 128, 0, s>>>(x, c_prev, h_prev, w, b, dh, dc, dgates_ws, dc_prev, B, H, W);
   BIN_CUDA_OK(cudaGetLastError());
-  const int chunk = 2048;
-  convlstm_bwd_weights_kernel<<<(unsigned)((total + chunk - 1) / chunk), 256, 0, s>>>(x, h_prev, dgates_ws, dw, db, B, H, W, chunk);
+  const unsigned wblocks = (unsigned)((total + 31) / 32 < 592 ? (total + 31) / 32 : 592);
+  convlstm_bwd_weights_kernel<<<wblocks, 288, 0, s>>>(x, h_prev, dgates_ws, dw, db, B, H, W);
   BIN_CUDA_OK(cudaGetLastError());
   convlstm_bwd_input_kernel<<<grid_for(total, 128), 128, 0, s>>>(dgates_ws, w, dx, dh_prev, B, H, W);
   BIN_CUDA_OK(cudaGetLastError());

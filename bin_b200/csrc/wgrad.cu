@@ -11,6 +11,10 @@
 // One MMA = 128(ci) x N(co) x 16 pixels (one 16-pixel tile row); a CTA keeps one fp32 accumulator per
 // tap in TMEM (taps x Cout <= 512 columns; wider layers run several tap groups), walks a slice of the
 // pixel tiles, and finally adds its partial sums into dW with fp32 atomics.
+// SX mode (the Cout=32 RDB convs): dW[ky][kx] = sum_p' dY[p'-(kx-1)] X[p'+(ky-1)*row], so the three kx taps
+// share the SAME X operand when dY is shifted instead: the dY tile is loaded three times at x offsets
+// +1, 0, -1 into consecutive plane groups and becomes one N = 96 operand (8 rows x 3 ky = 24 MMAs per tile
+// instead of 72 N=32 MMAs; the N=32 MMA is operand-fetch bound at 40 % of the math rate).
 #include <stdio.h>
 
 #include "common.cuh"
@@ -27,6 +31,7 @@ struct alignas(64) WgradParams {
   int dy_plane0, n;                                 // N = cout padded to 16
   int ks, pad, pw, rows;                            // X tile pitch (px) and rows incl. halo
   int tap0, ntaps;                                  // tap group handled by this launch
+  int sx;                                           // 3x3 / Cout=32: the 3 kx taps stacked into N (see below)
   int cout, cin;                                    // real sizes (flush bounds)
   int B, H, W, tiles_x, tiles_y, ntiles;
   int nstages;
@@ -54,7 +59,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x_plane_bytes = p.rows * p.pw * 16;
   const int x_bytes = 16 * x_plane_bytes;                       // 16 planes = 128 input channels
-  const int y_planes = p.n / 8;
+  const int y_planes = p.n / 8;                                 // SX: 3 shifted copies of the 4 dY planes
   const int y_plane_bytes = kWgTH * kWgTW * 16;
   const int y_bytes = y_planes * y_plane_bytes;
   const int stage_bytes = x_bytes + y_bytes;
@@ -99,10 +104,16 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         const bool seg1 = lp >= p.x0_planes;
         const void* tmap = seg1 ? (const void*)&p.xmap1 : (const void*)&p.xmap0;
         const int plane = seg1 ? p.x1_plane0 + (lp - p.x0_planes) : p.x0_plane0 + lp;
-        tma_load_4d(dst + (size_t)q * 4 * x_plane_bytes, tmap, &ctrl->full[s], (txi * kWgTW - p.pad) * 8,
+        tma_load_4d(dst + (size_t)q * 4 * x_plane_bytes, tmap, &ctrl->full[s], (txi * kWgTW - (p.sx ? 0 : p.pad)) * 8,
                     tyi * kWgTH - p.pad, plane, b);
       }
-      tma_load_4d(dst + x_bytes, &p.ymap, &ctrl->full[s], txi * kWgTW * 8, tyi * kWgTH, p.dy_plane0, b);
+      if (p.sx) {
+        for (int kx = 0; kx < 3; ++kx)
+          tma_load_4d(dst + x_bytes + kx * 4 * y_plane_bytes, &p.ymap, &ctrl->full[s], (txi * kWgTW + 1 - kx) * 8,
+                      tyi * kWgTH, p.dy_plane0, b);
+      } else {
+        tma_load_4d(dst + x_bytes, &p.ymap, &ctrl->full[s], txi * kWgTW * 8, tyi * kWgTH, p.dy_plane0, b);
+      }
       if (++s == S) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
@@ -117,7 +128,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
       const uint32_t yb = xb + x_bytes;
       if (elect_one()) {
         for (int tp = 0; tp < p.ntaps; ++tp) {
-          const int tap = p.tap0 + tp, ky = tap / p.ks, kx = tap % p.ks;
+          const int tap = p.tap0 + tp, ky = p.sx ? tp : tap / p.ks, kx = p.sx ? 0 : tap % p.ks;
           const uint32_t d = tmem_base + tp * p.n;
           for (int r = 0; r < kWgTH; ++r) {
             const uint64_t ad = umma_desc_mnmajor_noswz(xb + (uint32_t)((r + ky) * p.pw + kx) * 16, 128, x_plane_bytes);
@@ -150,8 +161,10 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         if (has_tiles && ci < p.cin) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int co = n0 + i;
-            if (co < p.cout) atomicAdd(p.dw + ((size_t)co * p.cin + ci) * kk + p.tap0 + tp, __uint_as_float(v[i]) * inv);
+            const int col = n0 + i;
+            const int co = p.sx ? (col & 31) : col;
+            const int tap = p.sx ? tp * 3 + (col >> 5) : p.tap0 + tp;
+            if (co < p.cout) atomicAdd(p.dw + ((size_t)co * p.cin + ci) * kk + tap, __uint_as_float(v[i]) * inv);
           }
         }
       }
@@ -168,16 +181,18 @@ int launch_wgrad_impl(const bin_act_t& x0, int x0_plane0, int x0_planes, const b
                       const bin_act_t& dy, int dy_plane0, int cout, int cin, int ks, const float* scale, float* dw,
                       cudaStream_t s) {
   if (ks != 1 && ks != 3 && ks != 5) return fail(BIN_ERR_ARG, "wgrad: ksize must be 1, 3 or 5");
-  const int n = (cout + 15) / 16 * 16;
+  int n = (cout + 15) / 16 * 16;
   if (n > 256) return fail(BIN_ERR_UNSUPPORTED, "wgrad: Cout > 256");
-  if (dy_plane0 + n / 8 > dy.planes) return fail(BIN_ERR_ARG, "wgrad: dY plane range exceeds tensor");
+  if (dy_plane0 + n / 8 > dy.planes) return fail(BIN_ERR_ARG, "wgrad: dY plane range exceeds tensor");   // (before SX widening)
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.pad = ks / 2; p.ks = ks;
-  p.pw = kWgTW + 2 * p.pad; p.rows = kWgTH + 2 * p.pad;
+  p.sx = (ks == 3 && cout == 32) ? 1 : 0;
+  if (p.sx) n = 96;                                   // MMA N = 3 shifted copies of the 32 dY channels
+  p.pw = kWgTW + (p.sx ? 0 : 2 * p.pad); p.rows = kWgTH + 2 * p.pad;
   BIN_TRY(make_p8_tmap_box(&p.xmap0, x0, p.pw, p.rows, 4));
   if (x1_planes > 0) BIN_TRY(make_p8_tmap_box(&p.xmap1, x1, p.pw, p.rows, 4));
-  BIN_TRY(make_p8_tmap_box(&p.ymap, dy, kWgTW, kWgTH, n / 8));
+  BIN_TRY(make_p8_tmap_box(&p.ymap, dy, kWgTW, kWgTH, p.sx ? 4 : n / 8));
   p.x0_plane0 = x0_plane0; p.x0_planes = x0_planes; p.x1_plane0 = x1_plane0; p.x1_planes = x1_planes;
   p.dy_plane0 = dy_plane0; p.n = n; p.cout = cout; p.cin = cin;
   p.B = x0.B; p.H = x0.H; p.W = x0.W;
@@ -195,7 +210,7 @@ int launch_wgrad_impl(const bin_act_t& x0, int x0_plane0, int x0_planes, const b
     BIN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     attr_done = true;
   }
-  const int kk = ks * ks;
+  const int kk = p.sx ? 3 : ks * ks;                  // SX: one accumulator per ky
   const int taps_per_group = 512 / n < kk ? 512 / n : kk;
   const int ci_planes = x0_planes + x1_planes;
   int grid = p.ntiles < 148 ? p.ntiles : 148;
