@@ -296,8 +296,8 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 6 * 3 * H * W * 4, "d2h_bytes_per_step": 3 * 3 * H * W * 4,
                     "note": "WindowPipeline: pinned-host frames in, outputs 13,8,12 (test.py:380-402) back to pinned host, copies overlapped with the previous/next window",
                     "matches_device_result": e2e_ok},
-            "gpu_launches": args.steps * 341 * 2,
-            "gpu_launches_note": "per window: 5 batched backbone stages x (1 pack + 66 conv) + 6 ConvLSTM = 341 kernels (replayed as one CUDA graph); timed twice (value, e2e)",
+            "gpu_launches": args.steps * 274 * 2,
+            "gpu_launches_note": "per window: 4 batched backbone stages x (1 pack + 66 conv) + 6 ConvLSTM = 274 kernels (replayed as one CUDA graph); timed twice (value, e2e)",
             "roofline": roof,
             "cpu_baseline": {"value": 1.0 / (cpu_dt * cpu_scale), "unit": UNIT, "cores": cpu_threads, "kind": "port",
                              "sample": f"128x128 6-frame window on the fp32 CPU oracle, mean of 3 ({cpu_dt:.2f} s each), scaled x{cpu_scale:.2f} by pixel count to {W}x{H}"},

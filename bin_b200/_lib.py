@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbin_b200.so")
 
-BIN_MAX_CALLS = 5
+BIN_MAX_CALLS = 6
 BIN_MAX_FRAMES = 5
 BIN_BACKBONE_NCONV = 66
 EPI_P8, EPI_PIXSHUF, EPI_FINAL = 0, 1, 2

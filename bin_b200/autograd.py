@@ -162,8 +162,8 @@ def window_apply(module, F):
     o = [None] * 14
     o[0], o[1], o[2], o[3], o[10] = backbone_stage(m1, [(F[0], F[1]), (F[1], F[2]), (F[2], F[3]), (F[3], F[4]), (F[4], F[5])])
     p4, p6, p8 = lstm(0, o[1]), lstm(1, o[2]), lstm(2, o[3])
-    o[4], o[5], o[6] = backbone_stage(m2, [(o[0], o[0], o[1]), (o[1], o[1], o[2]), (o[2], o[2], o[3])])
-    t0, t1, o[11] = backbone_stage(m2, [(p4, o[1], o[2]), (p6, o[2], o[3]), (p8, o[3], o[10])])
+    o[4], o[5], o[6], t0, t1, o[11] = backbone_stage(m2, [(o[0], o[0], o[1]), (o[1], o[1], o[2]), (o[2], o[2], o[3]),
+                                                          (p4, o[1], o[2]), (p6, o[2], o[3]), (p8, o[3], o[10])])
     p5, p7 = lstm(3, o[5]), lstm(4, o[6])
     o[7], o[8], t2, o[12] = backbone_stage(m3, [(o[4], F[1], o[4], o[5], F[2]), (o[5], F[2], o[5], o[6], F[3]),
                                               (p5, F[2], t0, t1, F[3]), (p7, F[3], t1, o[11], F[4])])

@@ -635,10 +635,10 @@ int bin_window_fwd(const bin_net_t* net, const float* const* F, float* const* o,
                                {{F[3], F[4]}, o[3]}, {{F[4], F[5]}, o[10]}}, B, H, W, bws, bws_bytes, s));
   // recurrent hand-off for the stage-1 outputs (RDN.py:451-453)
   BIN_TRY(lstm(0, o[1], p4)); BIN_TRY(lstm(1, o[2], p6)); BIN_TRY(lstm(2, o[3], p8));
-  // Stage 2: step 0 (RDN.py:384-386, "prev" slot duplicated) + step 1 (RDN.py:377-379)
-  BIN_TRY(run_stage(net, 1, 3, {{{o[0], o[0], o[1]}, o[4]}, {{o[1], o[1], o[2]}, o[5]}, {{o[2], o[2], o[3]}, o[6]}},
-                    B, H, W, bws, bws_bytes, s));
-  BIN_TRY(run_stage(net, 1, 3, {{{p4, o[1], o[2]}, t0}, {{p6, o[2], o[3]}, t1}, {{p8, o[3], o[10]}, o[11]}},
+  // Stage 2: step 0 (RDN.py:384-386, "prev" slot duplicated) + step 1 (RDN.py:377-379) in ONE launch of 6 calls:
+  // the step-1 calls only need stage-1 outputs and their ConvLSTM images, not step-0's stage 2.
+  BIN_TRY(run_stage(net, 1, 3, {{{o[0], o[0], o[1]}, o[4]}, {{o[1], o[1], o[2]}, o[5]}, {{o[2], o[2], o[3]}, o[6]},
+                               {{p4, o[1], o[2]}, t0}, {{p6, o[2], o[3]}, t1}, {{p8, o[3], o[10]}, o[11]}},
                     B, H, W, bws, bws_bytes, s));
   BIN_TRY(lstm(3, o[5], p5)); BIN_TRY(lstm(4, o[6], p7));                         // RDN.py:454-455
   // Stage 3: step 0 (RDN.py:387-388) + step 1 (RDN.py:380-381)

@@ -266,6 +266,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const int q = warp & 3;
     const int m = (warp - 4) >> 2;                      // which 128-row accumulator of the tile
     uint32_t acc_it = 0;
+    // FINAL epilogue: the mean of the input frames (RDN.py:221/279/333) of tile t+1 is loaded while tile t is being
+    // processed (one tile of software pipelining: a cold DRAM round trip per tile was the kernel's critical path).
+    constexpr int NFV = (EPI == BIN_EPI_FINAL) ? 3 * BIN_MAX_FRAMES : 1;
+    float fv[NFV];                                  // raw frame samples of the tile being processed
+    auto frame_load = [&](int tile_, float (&dst)[NFV]) {   // loads only: consumed one tile later
+      if constexpr (EPI == BIN_EPI_FINAL) {
+        int t = tile_ / p.nh;
+        const int txi_ = t % p.tiles_x; t /= p.tiles_x;
+        const int tyi_ = t % p.tiles_y;
+        const int b_ = p.b0 + t / p.tiles_y;
+        const int L_ = m * 128 + q * 32 + lane;
+        const int y_ = p.y0 + tyi_ * kTH + (L_ >> 5), x_ = txi_ * C::TW + (L_ & 31);
+        const bool valid_ = tile_ < p.ntiles && ((L_ & 31) < C::TW) && (y_ < p.y0 + p.ny) && (x_ < p.W);
+        const int call = b_ / p.fr.Bc, bb = b_ % p.fr.Bc;
+        const size_t hw = (size_t)p.H * p.W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const size_t off = ((size_t)bb * 3 + c) * hw + (size_t)y_ * p.W + x_;
+#pragma unroll
+          for (int fi = 0; fi < BIN_MAX_FRAMES; ++fi)
+            dst[c * BIN_MAX_FRAMES + fi] = (valid_ && fi < p.fr.nframes) ? __ldg(p.fr.frame[call][fi] + off) : 0.f;
+        }
+      }
+    };
+    frame_load(blockIdx.x, fv);
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++acc_it) {
       int t = tile;
       const int nh = t % p.nh; t /= p.nh;
@@ -274,6 +299,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const int b = p.b0 + t / p.tiles_y;
       const int yend = p.y0 + p.ny;
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
+      float fmean[(EPI == BIN_EPI_FINAL) ? 3 : 1];
+      if constexpr (EPI == BIN_EPI_FINAL) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float acc = fv[c * BIN_MAX_FRAMES];
+#pragma unroll
+          for (int fi = 1; fi < BIN_MAX_FRAMES; ++fi) acc += fv[c * BIN_MAX_FRAMES + fi];   // left-to-right like the reference
+          fmean[c] = acc / (float)p.fr.nframes;
+        }
+      }
+      frame_load(tile + (int)gridDim.x, fv);                      // next tile's samples: in flight during this tile's wait + stores
       const int L = m * 128 + q * 32 + lane;
       const int ty = L >> 5, tx = L & 31;
       const int y = p.y0 + tyi * kTH + ty, x = txi * C::TW + tx;
@@ -289,22 +325,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             rbuf[k] = (valid && (nh * NT) / 8 + k < p.store_planes) ? *reinterpret_cast<const uint4*>(p.res + off)
                                                                    : make_uint4(0, 0, 0, 0);
           }
-        }
-      }
-      // ... and the mean of the input frames (RDN.py:221/279/333)
-      float fmean[(EPI == BIN_EPI_FINAL) ? 3 : 1];
-      if constexpr (EPI == BIN_EPI_FINAL) {
-        const int call = b / p.fr.Bc, bb = b % p.fr.Bc;
-        const size_t hw = (size_t)p.H * p.W;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float acc = 0.f;
-          if (valid) {
-            const size_t off = ((size_t)bb * 3 + c) * hw + (size_t)y * p.W + x;
-            acc = p.fr.frame[call][0][off];
-            for (int fi = 1; fi < p.fr.nframes; ++fi) acc += p.fr.frame[call][fi][off];
-          }
-          fmean[c] = acc / (float)p.fr.nframes;
         }
       }
       if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 0);

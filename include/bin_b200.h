@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define BIN_ABI_VERSION 1
-#define BIN_MAX_CALLS 5   /* same-weight backbone calls batched along N */
+#define BIN_MAX_CALLS 6   /* same-weight backbone calls batched along N */
 #define BIN_MAX_FRAMES 5  /* frames per backbone call (2, 3 or 5) */
 
 enum { BIN_OK = 0, BIN_ERR_ARG = 1, BIN_ERR_CUDA = 2, BIN_ERR_UNSUPPORTED = 3, BIN_ERR_WORKSPACE = 4 };
