@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         }
       } else if constexpr (EPI == BIN_EPI_PIXSHUF) {
         // out[c, 2y+i, 2x+j] = conv[4c+2i+j, y, x]   (nn.PixelShuffle(2), RDN.py:206)
-#pragma unroll 1
+#pragma unroll 2
         for (int n0 = 0; n0 < NT; n0 += 32) {
           uint32_t v0[16], v1[16];
           tmem_ld16(taddr + n0, v0);

@@ -3,8 +3,8 @@
 set -x
 export BIN_B200_GRAPH=0
 mkdir -p gpurun_out
-# (1) launch list of ONE steady-state window: skip weight packing (4 backbones x 132) + window 0 (341)
-ncu --metrics gpu__time_duration.sum --clock-control none -s 869 -c 341 --csv \
+# (1) launch list of ONE steady-state window: skip weight packing (4 backbones x 132) + window 0 (274)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 802 -c 274 --csv \
     --log-file gpurun_out/launches_window.csv python tools/run_window.py 2 > gpurun_out/ncu_launch.log 2>&1
 # (2) full capture of the dominant kernel (x-stacked RDB conv), 3 launches from the steady state
 # conv launches only: window 0 = 330; window 1 stage 1 (5 batched calls): idx 2+5*i+c -> RDB 5 = 357..361

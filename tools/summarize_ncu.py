@@ -40,8 +40,8 @@ def launches():
         tot += v
     with open(os.path.join(P, f"{tag}_launches_window.md"), "w") as f:
         f.write(f"# {tag}: ncu launch list of ONE steady-state 6-frame 1280x720 window\n\n"
-                "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 869 -c 341 --csv python tools/run_window.py 2`\n"
-                "(BIN_B200_GRAPH=0; skip = 528 weight-pack launches + the 341 launches of window 0). Per-launch times under ncu are\n"
+                "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 802 -c 274 --csv python tools/run_window.py 2`\n"
+                "(BIN_B200_GRAPH=0; skip = 528 weight-pack launches + the 274 launches of window 0). Per-launch times under ncu are\n"
                 "cold-cache and serialised: compare SHARES, not absolutes.\n\n"
                 f"launches: {len(rows)}, sum of kernel durations: {tot/1e3:.2f} ms\n\n| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
