@@ -284,9 +284,10 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 storage / f32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
+            "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"bin_stage4 6-frame window {W}x{H} (SURVEY 8d config 2b; what test.py runs)",
                        "frames": 6, "windows_per_gpu_per_step": 1, "outputs": 14,
+                       "arithmetic": "fp16 operands / fp32 accumulate (tcgen05 kind::f16), fp32 frames in/out, fp32 ConvLSTM",
                        "l2": "per-step working set (>1 GB of activations per backbone stage) >> 126 MB L2; no explicit flush",
                        "executed_flop_fraction": EXECUTED_FRACTION, "weights": "synthetic U(+-1/sqrt(fan_in)) seed 0",
                        "weight_broadcast_ms": bcast_ms, "weight_broadcast_bytes": bcast_bytes},

@@ -60,6 +60,9 @@ class BackboneStageFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *gouts):
         model, ncalls, (B, H, W) = ctx.model, ctx.ncalls, ctx.shape
+        if ctx.save is None:
+            raise BinB200Error("bin_b200: backward through a backbone stage twice (retain_graph / double backward) is not "
+                               "supported: the saved activations are released after the first backward")
         n = model.NFRAMES
         dev = ctx.save.device
         with torch.cuda.device(dev):
