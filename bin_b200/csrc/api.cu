@@ -27,6 +27,8 @@ int launch_pack_bias(const float* b, int cout, int cout_pad, float* dst, cudaStr
 int launch_convlstm(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
                     float* h_out, float* c_out, int B, int H, int W, cudaStream_t s);
 int run_mma_bench(int n, int iters, int mode, float* cycles_host);
+int launch_tensor2img_u8(const float* x, int Hs, int Ws, int top, int left, int h, int w, uint8_t* out, cudaStream_t s);
+int launch_u8_to_frame(const uint8_t* img, int h, int w, int pl, int pr, int pt, int pb, float* out, cudaStream_t s);
 int launch_convlstm_bwd(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
                         const float* dh, const float* dc, float* dgates_ws, float* dx, float* dc_prev, float* dh_prev,
                         float* dw, float* db, int B, int H, int W, cudaStream_t s);
@@ -520,6 +522,14 @@ int bin_convlstm_fwd(const float* x, const float* c_prev, const float* h_prev, c
   return launch_convlstm(x, c_prev, h_prev, w, b, h_out, c_out, B, H, W, (cudaStream_t)s);
 }
 
+int bin_tensor2img_u8(const float* x, int Hs, int Ws, int top, int left, int h, int w, uint8_t* out, bin_stream_t s) {
+  if (!x || !out) return fail(BIN_ERR_ARG, "tensor2img: null argument");
+  return launch_tensor2img_u8(x, Hs, Ws, top, left, h, w, out, (cudaStream_t)s);
+}
+int bin_u8_to_frame(const uint8_t* img, int h, int w, int pad_l, int pad_r, int pad_t, int pad_b, float* out, bin_stream_t s) {
+  if (!img || !out) return fail(BIN_ERR_ARG, "u8_to_frame: null argument");
+  return launch_u8_to_frame(img, h, w, pad_l, pad_r, pad_t, pad_b, out, (cudaStream_t)s);
+}
 int bin_convlstm_bwd(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
                      const float* dh, const float* dc, float* dgates_ws, float* dx, float* dc_prev, float* dh_prev,
                      float* dw, float* db, int B, int H, int W, bin_stream_t s) {

@@ -304,6 +304,38 @@ __global__ void convlstm_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
+// ------------------------------------------------------------------ image boundary kernels
+// utils/util.py:113-137 tensor2img on one (3,Hs,Ws) fp32 RGB image + the crop of test.py:394-402:
+// clamp to [0,1], *255, round half to even (numpy .round()), uint8, HWC, BGR.
+__global__ void tensor2img_u8_kernel(const float* __restrict__ src, int Hs, int Ws, int top, int left, int h, int w,
+                                     uint8_t* __restrict__ dst) {
+  const size_t total = (size_t)h * w;
+  const size_t hws = (size_t)Hs * Ws;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = i % w, y = i / w;
+    const size_t so = (size_t)(y + top) * Ws + (x + left);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {                       // dst channel c = BGR -> source channel 2-c
+      const float v = fminf(fmaxf(src[(size_t)(2 - c) * hws + so], 0.f), 1.f);
+      dst[i * 3 + c] = (uint8_t)rintf(v * 255.0f);
+    }
+  }
+}
+// test.py:44-56 read_image (uint8 HWC BGR -> fp32 CHW RGB / 255) fused with the ReplicationPad2d of test.py:366-371.
+__global__ void u8_to_frame_kernel(const uint8_t* __restrict__ src, int h, int w, int pl, int pt, int Hp, int Wp,
+                                   float* __restrict__ dst) {
+  const size_t total = (size_t)Hp * Wp;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int X = i % Wp, Y = i / Wp;
+    int x = X - pl, y = Y - pt;
+    x = x < 0 ? 0 : (x >= w ? w - 1 : x);
+    y = y < 0 ? 0 : (y >= h ? h - 1 : y);
+    const uint8_t* px = src + ((size_t)y * w + x) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dst[(size_t)c * total + i] = (float)px[2 - c] / 255.f;
+  }
+}
+
 // ------------------------------------------------------------------ ConvLSTMCell backward (fp32)
 // Pass 1 (per pixel): recompute the gates (RDN.py:74-82), write d(gate pre-activations) [B,12,H,W] and dc_prev.
 __global__ void convlstm_bwd_gates_kernel(const float* __restrict__ x, const float* __restrict__ c_prev,
@@ -699,6 +731,19 @@ int launch_bias_grad(const bin_act_t& dy, int plane0, int C, const float* scale,
   const size_t hw = (size_t)dy.H * dy.W;
   dim3 grid(64, (C + 7) / 8);
   p8_bias_grad_kernel<<<grid, 256, 0, s>>>((const __half*)dy.ptr, dy.planes, plane0, C, dy.B, hw, scale, db);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_tensor2img_u8(const float* x, int Hs, int Ws, int top, int left, int h, int w, uint8_t* out, cudaStream_t s) {
+  if (top < 0 || left < 0 || h < 1 || w < 1 || top + h > Hs || left + w > Ws) return fail(BIN_ERR_ARG, "tensor2img: crop outside the image");
+  tensor2img_u8_kernel<<<grid_for((size_t)h * w, 256), 256, 0, s>>>(x, Hs, Ws, top, left, h, w, out);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_u8_to_frame(const uint8_t* img, int h, int w, int pl, int pr, int pt, int pb, float* out, cudaStream_t s) {
+  if (h < 1 || w < 1 || pl < 0 || pr < 0 || pt < 0 || pb < 0) return fail(BIN_ERR_ARG, "u8_to_frame: bad geometry");
+  const int Hp = h + pt + pb, Wp = w + pl + pr;
+  u8_to_frame_kernel<<<grid_for((size_t)Hp * Wp, 256), 256, 0, s>>>(img, h, w, pl, pt, Hp, Wp, out);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
 }

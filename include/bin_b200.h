@@ -175,6 +175,14 @@ int bin_window_fwd(const bin_net_t* net, const float* const* frames_host, float*
 int bin_pyramid3_fwd(const bin_net_t* net, const float* const* frames_host, float* const* outs_host, int B, int H,
                      int W, void* workspace, size_t workspace_bytes, bin_stream_t s);
 
+/* ---- image boundary of the caller loop ------------------------------------ */
+/* utils/util.py:113-137 tensor2img + the crop of test.py:394-402 for ONE (3,Hs,Ws) fp32 RGB image:
+ * clamp [0,1], *255, round-half-even, uint8 HWC BGR of the (top,left,h,w) window -> out (h*w*3 bytes, device). */
+int bin_tensor2img_u8(const float* x, int Hs, int Ws, int top, int left, int h, int w, uint8_t* out, bin_stream_t s);
+/* test.py:44-56 read_image + the ReplicationPad2d of test.py:366-371: uint8 HWC BGR (h,w,3) ->
+ * fp32 CHW RGB /255 of size (3, h+pad_t+pad_b, w+pad_l+pad_r), edge-replicated. */
+int bin_u8_to_frame(const uint8_t* img, int h, int w, int pad_l, int pad_r, int pad_t, int pad_b, float* out, bin_stream_t s);
+
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* Issue `iters` back-to-back tcgen05.mma (M=128, N=n, K=16, fp16) from one CTA per SM and
  * return cycles per MMA in *cycles_host (host pointer; synchronises). mode 0: A/B K-major

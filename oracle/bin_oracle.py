@@ -253,6 +253,23 @@ def psnr_u8(a: Tensor, b: Tensor) -> float:
     return 20.0 * math.log10(255.0 / math.sqrt(mse))
 
 
+def read_image_u8(img_bgr_u8):
+    """test.py:44-56 read_image on an already decoded uint8 HWC BGR array -> (3,H,W) fp32 RGB in [0,1]."""
+    import numpy as np
+    img = np.asarray(img_bgr_u8).astype(np.float32) / 255.
+    img = img[:, :, [2, 1, 0]]
+    return torch.from_numpy(np.ascontiguousarray(np.transpose(img, (2, 0, 1)))).float()
+
+
+def tensor2img_bgr_u8(t: Tensor):
+    """utils/util.py:113-137 tensor2img(tensor, np.uint8, (0,1)) for one (3,H,W) image -> uint8 HWC BGR numpy array."""
+    import numpy as np
+    t = t.squeeze().float().cpu().clamp(0, 1)
+    img = t.numpy()
+    img = np.transpose(img[[2, 1, 0], :, :], (1, 2, 0))
+    return (img * 255.0).round().astype(np.uint8)
+
+
 CONV_MACS_PER_PX_WINDOW = 14_234_976          # SURVEY §8d
 def window_flops(H: int, W: int, B: int = 1) -> float:
     return 2.0 * CONV_MACS_PER_PX_WINDOW * H * W * B

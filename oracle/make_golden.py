@@ -92,6 +92,13 @@ def main():
     save("convlstm.npz", x=x.numpy(), c0=c0.numpy(), h0=h0.numpy(),
          h_none=h1.numpy(), c_none=c1n.numpy(), h_state=h2.numpy(), c_state=c2n.numpy())
 
+    # -- tensor2img (utils/util.py:113-137), the image boundary of the caller loop --------
+    import utils.util as RU                    # the reference's own helper
+    g = torch.Generator().manual_seed(8)
+    t = torch.rand((3, 21, 34), generator=g) * 1.4 - 0.2
+    t.view(-1)[:6] = torch.tensor([0.5 / 255, 1.5 / 255, 2.5 / 255, 254.5 / 255, 1.0, 0.0])
+    save("tensor2img.npz", x=t.numpy(), out=RU.tensor2img(t.clone()))
+
     # -- backward: d(sum_k <out_k, cot_k>)/d(frames, a few params) (config 3) ----------
     net.train()
     fr = [f.requires_grad_(True) for f in O.synth_frames(6, 1, 16, 16, seed=9)]

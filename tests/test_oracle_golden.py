@@ -103,3 +103,8 @@ def test_window_grad(golden_dir, sd):
     for n, gr in zip(names, grads[6:]):
         ref = g["d:" + n]
         assert (gr - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()), n
+
+
+def test_tensor2img(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tensor2img.npz"))
+    assert np.array_equal(O.tensor2img_bgr_u8(torch.from_numpy(g["x"])), g["out"])
