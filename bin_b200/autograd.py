@@ -152,6 +152,15 @@ def pyramid_apply(pyr, B1, B3, B5, B7, B9, previous_input=None):
     return I2, I4, I6, I8, I3, I5, I7, I4b, I6b, I5c
 
 
+def pyramid3_apply(module, F):
+    """Stages 1-3 on 4 frames with autograd (BASELINE config 2a/3a; pattern of RDN.py:383-387)."""
+    pyr = module.model
+    o0, o1, o2 = backbone_stage(pyr.model1_1, [(F[0], F[1]), (F[1], F[2]), (F[2], F[3])])
+    o3, o4 = backbone_stage(pyr.model2_1, [(o0, o0, o1), (o1, o1, o2)])
+    (o5,) = backbone_stage(pyr.model3_1, [(o3, F[1], o3, o4, F[2])])
+    return o0, o1, o2, o3, o4, o5
+
+
 def window_apply(module, F):
     """Grad-enabled RDN_residual_interp_5_input_ConvLSTM_L.forward (RDN.py:422-465): the same 17 unique
     backbone calls / 6 live ConvLSTM calls as bin_window_fwd, each batched stage an autograd node."""

@@ -379,6 +379,10 @@ class RDN_residual_interp_5_input_ConvLSTM_L(nn.Module):
 
     def forward_pyramid3(self, B1, B3, B5, B7):
         """BASELINE config 2a: stages 1-3 on 4 frames -> [I2',I4',I6',I3',I5',I4'']."""
+        if torch.is_grad_enabled() and (any(f.requires_grad for f in (B1, B3, B5, B7)) or
+                                        any(p.requires_grad for p in self.model.parameters())):
+            from .autograd import pyramid3_apply                      # BASELINE config 3a (training on the 4-frame graph)
+            return pyramid3_apply(self, (B1, B3, B5, B7))
         frames = [f.contiguous() for f in (B1, B3, B5, B7)]
         B, H, W = _check_frames(frames)
         dev = frames[0].device

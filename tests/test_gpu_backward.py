@@ -171,3 +171,22 @@ def test_single_conv_dgrad_wgrad_exact(cin, cout, k, split):
                                scale.data_ptr(), dw.data_ptr(), st))
     torch.cuda.synchronize()
     assert (dw - gw_ref).abs().max().item() <= 1e-4 * gw_ref.abs().max().item()
+
+
+def test_pyramid3_training_config3a(net):
+    """BASELINE config 3a: fwd+bwd of the 4-frame 3-stage graph; frame gradients vs oracle autograd."""
+    sd = O.synth_state_dict(0)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("model.model")}
+    fr = [f.requires_grad_(True) for f in O.synth_frames(4, 1, 24, 40, seed=5)]
+    outs = O.pyramid3_4frames(fr, {**sd, **leaves})
+    cots = O.synth_frames(6, 1, 24, 40, seed=6)
+    loss = sum((o * (c - 0.5)).sum() for o, c in zip(outs, cots))
+    gref = torch.autograd.grad(loss, fr)
+    net.zero_grad(set_to_none=True)
+    frg = [f.detach().cuda().requires_grad_(True) for f in fr]
+    got = net.forward_pyramid3(*frg)
+    sum((o * (c.cuda() - 0.5)).sum() for o, c in zip(got, cots)).backward()
+    for k in range(4):
+        err = (frg[k].grad.cpu() - gref[k]).abs().max().item() / gref[k].abs().max().item()
+        assert err <= 0.03, (k, err)
+    assert net.model.model3_1.UPNet[2].weight.grad is not None and net.model.model4_1.UPNet[2].weight.grad is None

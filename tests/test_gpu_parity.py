@@ -133,6 +133,27 @@ def test_pyramid3_config2a(net, sd):
         assert (outs[k].cpu() - ref[k]).abs().max().item() <= TOL_FP16, k
 
 
+def test_config1_one_scale_on_four_frames(net, sd):
+    """BASELINE config 1: stage 1 only on the 3 adjacent pairs of a 4 x (1,3,64,64) window."""
+    fr = O.synth_frames(4, 1, 64, 64, seed=1234)
+    m1 = O.sub_sd(sd, "model.model1_1")
+    with torch.no_grad():
+        for a in range(3):
+            ref = O.backbone((fr[a], fr[a + 1]), m1)
+            got = net.model.model1_1(fr[a].cuda(), fr[a + 1].cuda()).cpu()
+            assert (got - ref).abs().max().item() <= TOL_FP16, a
+
+
+def test_dataparallel_wrapper_like_bin_model(net):
+    """bin_model.py:42 wraps netG in nn.DataParallel; with one visible device the wrapper calls the module directly."""
+    dp = torch.nn.DataParallel(net, device_ids=[0])
+    fr = [f.cuda() for f in O.synth_frames(6, 1, 32, 32, seed=2)]
+    with torch.no_grad():
+        a, b = dp(*fr), net(*fr)
+    assert len(a) == 14 and all(torch.equal(x, y) for x, y in zip(a, b))
+    assert dp.module is net
+
+
 def test_inputs_not_mutated_and_outputs_fresh(net):
     fr = [f.cuda() for f in O.synth_frames(6, 1, 32, 32, seed=2)]
     keep = [f.clone() for f in fr]
