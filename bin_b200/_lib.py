@@ -29,7 +29,7 @@ class ConvArgs(C.Structure):
                 ("in1", Act), ("in1_plane0", C.c_int), ("in1_planes", C.c_int),
                 ("w_packed", C.c_void_p), ("bias", C.c_void_p),
                 ("ksize", C.c_int), ("cout_pad", C.c_int), ("relu", C.c_int), ("epilogue", C.c_int), ("variant", C.c_int),
-                ("b_begin", C.c_int), ("b_count", C.c_int), ("y_begin", C.c_int), ("y_count", C.c_int), ("store_planes", C.c_int),
+                ("b_begin", C.c_int), ("b_count", C.c_int), ("y_begin", C.c_int), ("y_count", C.c_int), ("store_planes", C.c_int), ("x3", C.c_int),
                 ("out", Act), ("out_plane0", C.c_int),
                 ("res", Act), ("res_plane0", C.c_int),
                 ("fr", Frames)]
@@ -75,6 +75,13 @@ _SIGS = {
     "bin_window_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "bin_window_fwd": (C.c_int, [C.POINTER(Net), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                  C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "bin_backbone_packed_bytes_p": (C.c_size_t, [C.c_int, C.c_int]),
+    "bin_backbone_pack_p": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p]),
+    "bin_backbone_workspace_bytes_p": (C.c_size_t, [C.c_int] * 5),
+    "bin_backbone_fwd_p": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(Frames), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "bin_window_workspace_bytes_p": (C.c_size_t, [C.c_int] * 4),
+    "bin_window_fwd_p": (C.c_int, [C.POINTER(Net), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                   C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "bin_pyramid3_fwd": (C.c_int, [C.POINTER(Net), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "bin_tensor2img_u8": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),

@@ -20,9 +20,9 @@ int fail(int code, const std::string& msg) {
 
 int launch_nchw_to_p8(const float* x, int C, const bin_act_t& dst, int plane0, cudaStream_t s);
 int launch_p8_to_nchw(const bin_act_t& src, int plane0, int C, float* y, cudaStream_t s);
-int launch_pack_frames(const bin_frames_t& fr, int H, int W, const bin_act_t& dst, cudaStream_t s);
+int launch_pack_frames(const bin_frames_t& fr, int H, int W, const bin_act_t& dst, cudaStream_t s, int x3 = 0);
 int launch_pack_weight(const float* w, int cout, int cin, int ks, int cout_pad, int cin_pad, int variant,
-                       void* packed, cudaStream_t s);
+                       void* packed, cudaStream_t s, int x3 = 0);
 int launch_pack_bias(const float* b, int cout, int cout_pad, float* dst, cudaStream_t s);
 int launch_convlstm(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
                     float* h_out, float* c_out, int B, int H, int W, cudaStream_t s);
@@ -49,7 +49,7 @@ struct BackboneLayout {
   size_t bytes;
 };
 
-static BackboneLayout backbone_layout(int nframes) {
+static BackboneLayout backbone_layout(int nframes, int x3 = 0) {
   BackboneLayout L;
   int k = 0;
   auto add = [&](int cin, int cout, int ks, int cout_pad) {
@@ -74,7 +74,7 @@ static BackboneLayout backbone_layout(int nframes) {
   for (int i = 0; i < BIN_BACKBONE_NCONV; ++i) {
     ConvSpec& c = L.conv[i];
     c.w_off = off;
-    off = align_up(off + (size_t)c.cout_pad * c.cin_pad * c.ks * c.ks * sizeof(__half), 256);
+    off = align_up(off + (size_t)c.cout_pad * c.cin_pad * c.ks * c.ks * sizeof(__half) * (x3 ? 3 : 1), 256);
     c.b_off = off;
     off = align_up(off + (size_t)c.cout_pad * sizeof(float), 256);
   }
@@ -89,15 +89,15 @@ struct BackboneWs {
   bin_act_t x0, f1, f2, cat, g, t1, t2, u;
   size_t bytes;
 };
-static BackboneWs backbone_ws(int nframes, int Btot, int H, int W, void* base, bool train = false) {
+static BackboneWs backbone_ws(int nframes, int Btot, int H, int W, void* base, bool train = false, int x3 = 0) {
   BackboneWs w;
   const int h = H / 2, wd = W / 2;
   size_t off = 0;
   auto carve = [&](int planes, int hh, int ww) {
     bin_act_t t;
     t.ptr = base ? (void*)((uint8_t*)base + off) : nullptr;
-    t.B = Btot; t.planes = planes; t.H = hh; t.W = ww;
-    off = align_up(off + (size_t)Btot * planes * hh * ww * 16, 256);
+    t.B = Btot; t.planes = planes * (x3 ? 2 : 1); t.H = hh; t.W = ww;      // x3: hi + lo plane groups
+    off = align_up(off + (size_t)Btot * t.planes * hh * ww * 16, 256);
     return t;
   };
   w.x0 = carve((int)align_up(12 * nframes, kKC) / 8, h, wd);
@@ -112,9 +112,10 @@ static BackboneWs backbone_ws(int nframes, int Btot, int H, int W, void* base, b
   return w;
 }
 
-static bin_conv_args_t conv_args(const void* blob, const ConvSpec& c) {
+static bin_conv_args_t conv_args(const void* blob, const ConvSpec& c, int x3 = 0) {
   bin_conv_args_t a;
   memset(&a, 0, sizeof(a));
+  a.x3 = x3;
   a.w_packed = (const uint8_t*)blob + c.w_off;
   a.bias = (const float*)((const uint8_t*)blob + c.b_off);
   a.ksize = c.ks;
@@ -193,12 +194,12 @@ static std::vector<Band> plan_bands(int Btot, int h, int w) {
 // One RDB: 4 x (conv3x3+ReLU -> growth planes) + LFF 1x1 + residual (RDN.py:149-165).
 static int run_rdb(const void* blob, const BackboneLayout& L, int i, const bin_act_t& xin, int x_plane0,
                    const bin_act_t& g, const bin_act_t& out, int out_plane0, const std::vector<Band>& bands,
-                   cudaStream_t s, int g_plane0 = 0) {
+                   cudaStream_t s, int g_plane0 = 0, int x3 = 0) {
   const int base = 2 + i * (kCgrow + 1);
   const int h = xin.H;
   for (const Band& bd : bands) {
     for (int c = 0; c < kCgrow; ++c) {
-      bin_conv_args_t a = conv_args(blob, L.conv[base + c]);
+      bin_conv_args_t a = conv_args(blob, L.conv[base + c], x3);
       a.in0 = xin; a.in0_plane0 = x_plane0; a.in0_planes = 12;
       a.in1 = g; a.in1_plane0 = g_plane0; a.in1_planes = 4 * c;
       a.relu = 1; a.epilogue = BIN_EPI_P8;
@@ -208,7 +209,7 @@ static int run_rdb(const void* blob, const BackboneLayout& L, int i, const bin_a
       a.b_begin = bd.b0; a.b_count = bd.nb; a.y_begin = lo; a.y_count = hi - lo;
       BIN_TRY(launch_conv(a, s));
     }
-    bin_conv_args_t a = conv_args(blob, L.conv[base + kCgrow]);
+    bin_conv_args_t a = conv_args(blob, L.conv[base + kCgrow], x3);
     a.in0 = xin; a.in0_plane0 = x_plane0; a.in0_planes = 12;
     a.in1 = g; a.in1_plane0 = g_plane0; a.in1_planes = 16;
     a.epilogue = BIN_EPI_P8;
@@ -221,50 +222,51 @@ static int run_rdb(const void* blob, const BackboneLayout& L, int i, const bin_a
 }
 
 static int run_backbone(int nframes, const void* blob, const bin_frames_t& fr, int H, int W, void* workspace,
-                        size_t workspace_bytes, cudaStream_t s, bool train = false) {
+                        size_t workspace_bytes, cudaStream_t s, bool train = false, int x3 = 0) {
   if (!valid_nframes(nframes) || fr.nframes != nframes) return fail(BIN_ERR_ARG, "backbone: nframes must be 2, 3 or 5");
   if (fr.ncalls < 1 || fr.ncalls > BIN_MAX_CALLS || fr.Bc < 1) return fail(BIN_ERR_ARG, "backbone: bad call table");
   if ((H & 1) || (W & 1) || H < 2 || W < 2) return fail(BIN_ERR_ARG, "backbone: H and W must be even (RDN.py:123-128)");
   const int Btot = fr.ncalls * fr.Bc;
-  const BackboneLayout L = backbone_layout(nframes);
-  const BackboneWs ws = backbone_ws(nframes, Btot, H, W, workspace, train);
+  if (train && x3) return fail(BIN_ERR_UNSUPPORTED, "backbone: training runs in the fp16 mode only");
+  const BackboneLayout L = backbone_layout(nframes, x3);
+  const BackboneWs ws = backbone_ws(nframes, Btot, H, W, workspace, train, x3);
   if (ws.bytes > workspace_bytes) return fail(BIN_ERR_WORKSPACE, "backbone: workspace too small");
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(BIN_ERR_ARG, "backbone: workspace must be 256-byte aligned");
 
-  BIN_TRY(launch_pack_frames(fr, H, W, ws.x0, s));                               // RDN.py:211
+  BIN_TRY(launch_pack_frames(fr, H, W, ws.x0, s, x3));                           // RDN.py:211
   {
-    bin_conv_args_t a = conv_args(blob, L.conv[0]);                              // SFENet1 (RDN.py:212)
-    a.in0 = ws.x0; a.in0_planes = ws.x0.planes; a.epilogue = BIN_EPI_P8; a.out = ws.f1;
+    bin_conv_args_t a = conv_args(blob, L.conv[0], x3);                              // SFENet1 (RDN.py:212)
+    a.in0 = ws.x0; a.in0_planes = ws.x0.planes / (x3 ? 2 : 1); a.epilogue = BIN_EPI_P8; a.out = ws.f1;
     BIN_TRY(launch_conv(a, s));
   }
   {
-    bin_conv_args_t a = conv_args(blob, L.conv[1]);                              // SFENet2 (RDN.py:213)
+    bin_conv_args_t a = conv_args(blob, L.conv[1], x3);                              // SFENet2 (RDN.py:213)
     a.in0 = ws.f1; a.in0_planes = 12; a.epilogue = BIN_EPI_P8; a.out = ws.f2;
     BIN_TRY(launch_conv(a, s));
   }
   const std::vector<Band> bands = plan_bands(Btot, H / 2, W / 2);
   for (int i = 0; i < kD; ++i) {                                                 // RDN.py:215-217
     const int gp0 = train ? 16 * i : 0;
-    if (i == 0) BIN_TRY(run_rdb(blob, L, i, ws.f2, 0, ws.g, ws.cat, 0, bands, s, gp0));
-    else BIN_TRY(run_rdb(blob, L, i, ws.cat, 12 * (i - 1), ws.g, ws.cat, 12 * i, bands, s, gp0));
+    if (i == 0) BIN_TRY(run_rdb(blob, L, i, ws.f2, 0, ws.g, ws.cat, 0, bands, s, gp0, x3));
+    else BIN_TRY(run_rdb(blob, L, i, ws.cat, 12 * (i - 1), ws.g, ws.cat, 12 * i, bands, s, gp0, x3));
   }
   {
-    bin_conv_args_t a = conv_args(blob, L.conv[62]);                             // GFF.0 on the 1152-ch concat (RDN.py:218)
+    bin_conv_args_t a = conv_args(blob, L.conv[62], x3);                             // GFF.0 on the 1152-ch concat (RDN.py:218)
     a.in0 = ws.cat; a.in0_planes = 12 * kD; a.epilogue = BIN_EPI_P8; a.out = ws.t1;
     BIN_TRY(launch_conv(a, s));
   }
   {
-    bin_conv_args_t a = conv_args(blob, L.conv[63]);                             // GFF.1, x += f__1 (RDN.py:219)
+    bin_conv_args_t a = conv_args(blob, L.conv[63], x3);                             // GFF.1, x += f__1 (RDN.py:219)
     a.in0 = ws.t1; a.in0_planes = 12; a.epilogue = BIN_EPI_P8; a.out = ws.t2; a.res = ws.f1;
     BIN_TRY(launch_conv(a, s));
   }
   {
-    bin_conv_args_t a = conv_args(blob, L.conv[64]);                             // UPNet.0 + PixelShuffle (RDN.py:205-206)
+    bin_conv_args_t a = conv_args(blob, L.conv[64], x3);                             // UPNet.0 + PixelShuffle (RDN.py:205-206)
     a.in0 = ws.t2; a.in0_planes = 12; a.epilogue = BIN_EPI_PIXSHUF; a.out = ws.u;
     BIN_TRY(launch_conv(a, s));
   }
   {
-    bin_conv_args_t a = conv_args(blob, L.conv[65]);                             // UPNet.2 + mean(frames) (RDN.py:207,221)
+    bin_conv_args_t a = conv_args(blob, L.conv[65], x3);                             // UPNet.2 + mean(frames) (RDN.py:207,221)
     a.in0 = ws.u; a.in0_planes = 8; a.epilogue = BIN_EPI_FINAL; a.fr = fr;
     BIN_TRY(launch_conv(a, s));
   }
@@ -447,7 +449,7 @@ struct Call {
   float* out;
 };
 static int run_stage(const bin_net_t* net, int which, int nframes, const std::vector<Call>& calls, int B, int H, int W,
-                     void* ws, size_t ws_bytes, cudaStream_t s) {
+                     void* ws, size_t ws_bytes, cudaStream_t s, int x3 = 0) {
   bin_frames_t fr;
   memset(&fr, 0, sizeof(fr));
   fr.ncalls = (int)calls.size(); fr.nframes = nframes; fr.Bc = B;
@@ -455,14 +457,14 @@ static int run_stage(const bin_net_t* net, int which, int nframes, const std::ve
     for (int f = 0; f < nframes; ++f) fr.frame[k][f] = calls[k].in[f];
     fr.out[k] = calls[k].out;
   }
-  return run_backbone(nframes, net->blob[which], fr, H, W, ws, ws_bytes, s);
+  return run_backbone(nframes, net->blob[which], fr, H, W, ws, ws_bytes, s, false, x3);
 }
 
-static size_t window_ws_bytes(int B, int H, int W, int max_calls, int ntemp) {
+static size_t window_ws_bytes(int B, int H, int W, int max_calls, int ntemp, int x3 = 0) {
   size_t bb = 0;
   const int nf[3] = {2, 3, 5};
   for (int i = 0; i < 3; ++i) {
-    size_t v = backbone_ws(nf[i], max_calls * B, H, W, nullptr).bytes;
+    size_t v = backbone_ws(nf[i], max_calls * B, H, W, nullptr, false, x3).bytes;
     bb = v > bb ? v : bb;
   }
   return bb + (size_t)ntemp * align_up((size_t)B * 3 * H * W * sizeof(float), 256);
@@ -621,13 +623,11 @@ int bin_rdb_fwd(const void* blob, int nframes, int index, const float* x, float*
   return launch_p8_to_nchw(out, 0, kG0, y, (cudaStream_t)s);
 }
 
-size_t bin_window_workspace_bytes(int B, int H, int W) { return window_ws_bytes(B, H, W, BIN_MAX_CALLS, 9); }
-
-int bin_window_fwd(const bin_net_t* net, const float* const* F, float* const* o, int B, int H, int W, void* workspace,
-                   size_t workspace_bytes, bin_stream_t s_) {
+static int window_fwd_impl(const bin_net_t* net, const float* const* F, float* const* o, int B, int H, int W, void* workspace,
+                           size_t workspace_bytes, bin_stream_t s_, int x3) {
   if (!net || !F || !o) return fail(BIN_ERR_ARG, "window_fwd: null argument");
   cudaStream_t s = (cudaStream_t)s_;
-  const size_t need = window_ws_bytes(B, H, W, BIN_MAX_CALLS, 9);
+  const size_t need = window_ws_bytes(B, H, W, BIN_MAX_CALLS, 9, x3);
   if (workspace_bytes < need) return fail(BIN_ERR_WORKSPACE, "window_fwd: workspace too small");
   const size_t fbytes = align_up((size_t)B * 3 * H * W * sizeof(float), 256);
   uint8_t* base = (uint8_t*)workspace;
@@ -642,24 +642,58 @@ int bin_window_fwd(const bin_net_t* net, const float* const* F, float* const* o,
   };
   // Stage 1 (RDN.py:371-374): 4 calls of step 0 + the one stage-1 call of step 1 that is not a repeat.
   BIN_TRY(run_stage(net, 0, 2, {{{F[0], F[1]}, o[0]}, {{F[1], F[2]}, o[1]}, {{F[2], F[3]}, o[2]},
-                               {{F[3], F[4]}, o[3]}, {{F[4], F[5]}, o[10]}}, B, H, W, bws, bws_bytes, s));
+                               {{F[3], F[4]}, o[3]}, {{F[4], F[5]}, o[10]}}, B, H, W, bws, bws_bytes, s, x3));
   // recurrent hand-off for the stage-1 outputs (RDN.py:451-453)
   BIN_TRY(lstm(0, o[1], p4)); BIN_TRY(lstm(1, o[2], p6)); BIN_TRY(lstm(2, o[3], p8));
   // Stage 2: step 0 (RDN.py:384-386, "prev" slot duplicated) + step 1 (RDN.py:377-379) in ONE launch of 6 calls:
   // the step-1 calls only need stage-1 outputs and their ConvLSTM images, not step-0's stage 2.
   BIN_TRY(run_stage(net, 1, 3, {{{o[0], o[0], o[1]}, o[4]}, {{o[1], o[1], o[2]}, o[5]}, {{o[2], o[2], o[3]}, o[6]},
                                {{p4, o[1], o[2]}, t0}, {{p6, o[2], o[3]}, t1}, {{p8, o[3], o[10]}, o[11]}},
-                    B, H, W, bws, bws_bytes, s));
+                    B, H, W, bws, bws_bytes, s, x3));
   BIN_TRY(lstm(3, o[5], p5)); BIN_TRY(lstm(4, o[6], p7));                         // RDN.py:454-455
   // Stage 3: step 0 (RDN.py:387-388) + step 1 (RDN.py:380-381)
   BIN_TRY(run_stage(net, 2, 5, {{{o[4], F[1], o[4], o[5], F[2]}, o[7]}, {{o[5], F[2], o[5], o[6], F[3]}, o[8]},
                                {{p5, F[2], t0, t1, F[3]}, t2}, {{p7, F[3], t1, o[11], F[4]}, o[12]}},
-                    B, H, W, bws, bws_bytes, s));
+                    B, H, W, bws, bws_bytes, s, x3));
   BIN_TRY(lstm(5, o[8], p6b));                                                    // RDN.py:456
   // Stage 4: step 0 (RDN.py:389) + step 1 (RDN.py:382)
   BIN_TRY(run_stage(net, 3, 5, {{{o[1], o[1], o[7], o[8], o[2]}, o[9]}, {{p6b, o[2], t2, o[12], o[3]}, o[13]}},
-                    B, H, W, bws, bws_bytes, s));
+                    B, H, W, bws, bws_bytes, s, x3));
   return BIN_OK;
+}
+
+size_t bin_window_workspace_bytes(int B, int H, int W) { return window_ws_bytes(B, H, W, BIN_MAX_CALLS, 9); }
+int bin_window_fwd(const bin_net_t* net, const float* const* F, float* const* o, int B, int H, int W, void* workspace,
+                   size_t workspace_bytes, bin_stream_t s) {
+  return window_fwd_impl(net, F, o, B, H, W, workspace, workspace_bytes, s, 0);
+}
+/* precision-parameterised twins (BIN_PREC_*) */
+size_t bin_window_workspace_bytes_p(int B, int H, int W, int prec) { return window_ws_bytes(B, H, W, BIN_MAX_CALLS, 9, prec ? 1 : 0); }
+int bin_window_fwd_p(const bin_net_t* net, const float* const* F, float* const* o, int B, int H, int W, void* workspace,
+                     size_t workspace_bytes, int prec, bin_stream_t s) {
+  return window_fwd_impl(net, F, o, B, H, W, workspace, workspace_bytes, s, prec ? 1 : 0);
+}
+size_t bin_backbone_packed_bytes_p(int nframes, int prec) { return valid_nframes(nframes) ? backbone_layout(nframes, prec ? 1 : 0).bytes : 0; }
+int bin_backbone_pack_p(int nframes, const float* const* w_host, const float* const* b_host, void* blob, int prec,
+                        bin_stream_t s) {
+  if (!valid_nframes(nframes)) return fail(BIN_ERR_ARG, "backbone_pack: nframes must be 2, 3 or 5");
+  const int x3 = prec ? 1 : 0;
+  const BackboneLayout L = backbone_layout(nframes, x3);
+  for (int i = 0; i < BIN_BACKBONE_NCONV; ++i) {
+    const ConvSpec& c = L.conv[i];
+    BIN_TRY(launch_pack_weight(w_host[i], c.cout, c.cin, c.ks, c.cout_pad, c.cin_pad, BIN_CONV_DEFAULT,
+                               (uint8_t*)blob + c.w_off, (cudaStream_t)s, x3));
+    BIN_TRY(launch_pack_bias(b_host[i], c.cout, c.cout_pad, (float*)((uint8_t*)blob + c.b_off), (cudaStream_t)s));
+  }
+  return BIN_OK;
+}
+size_t bin_backbone_workspace_bytes_p(int nframes, int Btot, int H, int W, int prec) {
+  return valid_nframes(nframes) ? backbone_ws(nframes, Btot, H, W, nullptr, false, prec ? 1 : 0).bytes : 0;
+}
+int bin_backbone_fwd_p(int nframes, const void* blob, const bin_frames_t* fr, int H, int W, void* workspace,
+                       size_t workspace_bytes, int prec, bin_stream_t s) {
+  if (!fr || !blob) return fail(BIN_ERR_ARG, "backbone_fwd: null argument");
+  return run_backbone(nframes, blob, *fr, H, W, workspace, workspace_bytes, (cudaStream_t)s, false, prec ? 1 : 0);
 }
 
 int bin_pyramid3_fwd(const bin_net_t* net, const float* const* F, float* const* o, int B, int H, int W,

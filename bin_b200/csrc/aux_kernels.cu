@@ -42,7 +42,7 @@ __global__ void p8_to_nchw_kernel(const __half* __restrict__ src, int planes, in
 // Reference: RDN.py:211/269/323 torch.cat(frames,1) then pixel_reshuffle(.,2) (RDN.py:107-132):
 // packed channel = (f*3+rgb)*4 + dy*2 + dx for pixel (2y+dy, 2x+dx); zero-padded to dst.planes*8.
 __global__ void pack_frames_kernel(const __grid_constant__ bin_frames_t fr, int H, int W, __half* __restrict__ dst,
-                                   int planes) {
+                                   int planes, int x3) {   // planes = LOGICAL planes; x3: dst holds hi/lo groups of 4
   const int h = H / 2, w = W / 2;
   const int Btot = fr.ncalls * fr.Bc;
   const size_t total = (size_t)Btot * planes * h * w;
@@ -53,7 +53,7 @@ __global__ void pack_frames_kernel(const __grid_constant__ bin_frames_t fr, int 
     const int pl = (i / ((size_t)w * h)) % planes;
     const int b = i / ((size_t)w * h * planes);
     const int call = b / fr.Bc, bb = b % fr.Bc;
-    __align__(16) __half v[8];
+    float fv[8];
 #pragma unroll
     for (int half8 = 0; half8 < 2; ++half8) {          // 4 packed channels = one (frame, rgb) 2x2 patch
       const int c4 = pl * 2 + half8;                   // index of the (f,rgb) pair
@@ -62,17 +62,24 @@ __global__ void pack_frames_kernel(const __grid_constant__ bin_frames_t fr, int 
         const float* src = fr.frame[call][f] + (((size_t)bb * 3 + rgb) * H + 2 * y) * W + 2 * x;
         const float2 r0 = *reinterpret_cast<const float2*>(src);
         const float2 r1 = *reinterpret_cast<const float2*>(src + W);
-        v[half8 * 4 + 0] = __float2half_rn(r0.x);
-        v[half8 * 4 + 1] = __float2half_rn(r0.y);
-        v[half8 * 4 + 2] = __float2half_rn(r1.x);
-        v[half8 * 4 + 3] = __float2half_rn(r1.y);
+        fv[half8 * 4 + 0] = r0.x; fv[half8 * 4 + 1] = r0.y; fv[half8 * 4 + 2] = r1.x; fv[half8 * 4 + 3] = r1.y;
       } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[half8 * 4 + e] = __float2half_rn(0.f);
+        for (int e = 0; e < 4; ++e) fv[half8 * 4 + e] = 0.f;
       }
     }
-    const size_t off = ((((size_t)b * planes + pl) * h + y) * w + x) * 8;
+    __align__(16) __half v[8];
+    __align__(16) __half vl[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = __float2half_rn(fv[e]);
+      vl[e] = __float2half_rn(fv[e] - __half2float(v[e]));
+    }
+    const int pplanes = x3 ? 2 * planes : planes;
+    const int pp = x3 ? 2 * (pl & ~3) + (pl & 3) : pl;
+    const size_t off = ((((size_t)b * pplanes + pp) * h + y) * w + x) * 8;
     *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(v);
+    if (x3) *reinterpret_cast<uint4*>(dst + off + (size_t)4 * h * w * 8) = *reinterpret_cast<const uint4*>(vl);
   }
 }
 
@@ -80,11 +87,14 @@ __global__ void pack_frames_kernel(const __grid_constant__ bin_frames_t fr, int 
 // OIHW fp32 -> [nh][chunk][ky][kx][4][NT][8] fp16, or (stackx) [chunk][ky][4][kx*cout_pad+co][8].
 // transpose != 0 packs the data-gradient weights instead: V[co'][ci'][ky][kx] = W[ci'][row0+co'][k-1-ky][k-1-kx]
 // (a conv with V over dY gives dX for stride-1 / pad k/2 convs), co' < nrows, ci' < cout.
+// x3 != 0 (BIN_PREC_F32X3): three slabs per logical chunk -- hi, hi, lo of (w * 2^8) -- matching the kernel's
+// x_hi*W_hi + x_lo*W_hi + x_hi*W_lo chunk order.
 __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, int ks, int cout_pad, int cin_pad,
-                                   int nt, int stackx, int transpose, int row0, int nrows,
+                                   int nt, int stackx, int transpose, int row0, int nrows, int x3,
                                    __half* __restrict__ dst) {
-  const size_t total = (size_t)cout_pad * cin_pad * ks * ks;
-  const int nchunks = cin_pad / kKC;
+  const int rep = x3 ? 3 : 1;
+  const size_t total = (size_t)cout_pad * cin_pad * ks * ks * rep;
+  const int nchunks = (cin_pad / kKC) * rep;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t t = i;
     int e, kp, kx, ky, ch, co;
@@ -103,14 +113,20 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
       ch = t % nchunks; t /= nchunks;
       co = (int)t * nt + n;
     }
-    const int ci = ch * kKC + kp * 8 + e;
+    const int ci = (ch / rep) * kKC + kp * 8 + e;
     float v = 0.f;
     if (!transpose) {
       if (co < cout && ci < cin) v = w[(((size_t)co * cin + ci) * ks + ky) * ks + kx];
     } else {
       if (co < nrows && ci < cout) v = w[(((size_t)ci * cin + row0 + co) * ks + (ks - 1 - ky)) * ks + (ks - 1 - kx)];
     }
-    dst[i] = __float2half_rn(v);
+    if (x3) {
+      v *= 256.f;
+      const __half hi = __float2half_rn(v);
+      dst[i] = (ch % 3) < 2 ? hi : __float2half_rn(v - __half2float(hi));
+    } else {
+      dst[i] = __float2half_rn(v);
+    }
   }
 }
 
@@ -646,26 +662,27 @@ int launch_p8_to_nchw(const bin_act_t& src, int plane0, int C, float* y, cudaStr
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
 }
-int launch_pack_frames(const bin_frames_t& fr, int H, int W, const bin_act_t& dst, cudaStream_t s) {
+int launch_pack_frames(const bin_frames_t& fr, int H, int W, const bin_act_t& dst, cudaStream_t s, int x3) {
   if ((H & 1) || (W & 1)) return fail(BIN_ERR_ARG, "frame height/width must be even (pixel_reshuffle, RDN.py:123-128)");
   if (fr.ncalls < 1 || fr.ncalls > BIN_MAX_CALLS || fr.nframes < 1 || fr.nframes > BIN_MAX_FRAMES)
     return fail(BIN_ERR_ARG, "pack_frames: bad frame table");
-  if (dst.B != fr.ncalls * fr.Bc || dst.H != H / 2 || dst.W != W / 2 || dst.planes * 8 < 12 * fr.nframes)
+  const int lplanes = x3 ? dst.planes / 2 : dst.planes;
+  if (dst.B != fr.ncalls * fr.Bc || dst.H != H / 2 || dst.W != W / 2 || lplanes * 8 < 12 * fr.nframes || (x3 && (lplanes & 3)))
     return fail(BIN_ERR_ARG, "pack_frames: destination geometry mismatch");
-  const size_t total = (size_t)dst.B * dst.planes * dst.H * dst.W;
-  pack_frames_kernel<<<grid_for(total, 256), 256, 0, s>>>(fr, H, W, (__half*)dst.ptr, dst.planes);
+  const size_t total = (size_t)dst.B * lplanes * dst.H * dst.W;
+  pack_frames_kernel<<<grid_for(total, 256), 256, 0, s>>>(fr, H, W, (__half*)dst.ptr, lplanes, x3);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
 }
 int launch_pack_weight(const float* w, int cout, int cin, int ks, int cout_pad, int cin_pad, int variant,
-                       void* packed, cudaStream_t s) {
+                       void* packed, cudaStream_t s, int x3) {
   if (cin_pad % kKC || cout_pad % 16 || cout > cout_pad || cin > cin_pad)
     return fail(BIN_ERR_ARG, "pack_conv_weight: cin_pad must be a multiple of 32, cout_pad of 16");
   const int nt = conv_nt(cout_pad);
   if (cout_pad % nt) return fail(BIN_ERR_ARG, "pack_conv_weight: cout_pad must be <=128, or a multiple of 96 or 128");
-  const size_t total = (size_t)cout_pad * cin_pad * ks * ks;
+  const size_t total = (size_t)cout_pad * cin_pad * ks * ks * (x3 ? 3 : 1);
   const int stackx = (ks == 3 && (cout_pad == 32 || cout_pad == 16) && variant == BIN_CONV_DEFAULT) ? 1 : 0;
-  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, cout, cin, ks, cout_pad, cin_pad, nt, stackx, 0, 0, 0,
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, cout, cin, ks, cout_pad, cin_pad, nt, stackx, 0, 0, 0, x3,
                                                           (__half*)packed);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
@@ -677,7 +694,7 @@ int launch_pack_weight_t(const float* w, int cout, int cin, int ks, int row0, in
   if (cin_pad_t % kKC || cout_pad_t % 96 || nrows > cout_pad_t || cout > cin_pad_t || row0 + nrows > cin)
     return fail(BIN_ERR_ARG, "pack_conv_weight_t: bad padding / row range");
   const size_t total = (size_t)cout_pad_t * cin_pad_t * ks * ks;
-  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, cout, cin, ks, cout_pad_t, cin_pad_t, 96, 0, 1, row0, nrows,
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, cout, cin, ks, cout_pad_t, cin_pad_t, 96, 0, 1, row0, nrows, 0,
                                                           (__half*)packed);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;

@@ -101,7 +101,29 @@ constexpr int kThreads = 384;   // 12 warps, see the role table below
 // TMEM accumulator buffers alternate per tile and are released by the epilogue (tmem_full counts
 // one tcgen05.commit per MMA warp).
 // A pipeline stage holds up to p.cps "units" (unit = one 32-channel chunk, or one (chunk, ky) for 5x5).
-template <int NT, int KS, int EPI, bool SX>
+// X3 ("fp32-accurate" mode, 1e-5 parity bar): every value is carried as an fp16 pair hi + lo (22 significant bits).
+// Tensors hold, per 32-channel chunk, 4 planes of hi followed by 4 planes of lo; a logical K chunk becomes three
+// physical chunks  x_hi*W_hi + x_lo*W_hi + x_hi*W_lo  (the lo*lo term is below 2^-22), the weights are packed
+// pre-scaled by 2^8 so that W_lo stays a normal fp16 number, and the epilogue un-scales the fp32 accumulator and
+// splits its result into (hi, lo) again.  Same kernel, same descriptors: 3x the MMAs, 2x the activation bytes.
+__device__ __forceinline__ int x3_plane(int logical_plane) { return 2 * (logical_plane & ~3) + (logical_plane & 3); }
+__device__ __forceinline__ void split_store(__half* base_hi, __half* base_lo, const float* f) {
+  uint4 hi, lo;
+  uint32_t* hp = reinterpret_cast<uint32_t*>(&hi);
+  uint32_t* lp = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half h0 = __float2half_rn(f[2 * i]), h1 = __float2half_rn(f[2 * i + 1]);
+    const __half2 hh = __halves2half2(h0, h1);
+    const __half2 ll = __floats2half2_rn(f[2 * i] - __half2float(h0), f[2 * i + 1] - __half2float(h1));
+    hp[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    lp[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  *reinterpret_cast<uint4*>(base_hi) = hi;
+  *reinterpret_cast<uint4*>(base_lo) = lo;
+}
+
+template <int NT, int KS, int EPI, bool SX, bool X3>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using C = ConvCfg<NT, KS, SX>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -178,9 +200,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           mbar_expect_tx(&ctrl->full[s], (uint32_t)(nu * unit_bytes));
           for (int u = 0; u < nu; ++u) {
             const int c = (unit + u) / C::NSUB, sub = (unit + u) % C::NSUB;
-            const bool seg1 = c >= p.nch0;
+            const int lc = X3 ? c / 3 : c;                     // logical 32-channel chunk
+            const bool seg1 = lc >= p.nch0l;
             const void* tmap = seg1 ? (const void*)&p.tmap1 : (const void*)&p.tmap0;
-            const int plane = seg1 ? p.plane0_1 + (c - p.nch0) * kKPL : p.plane0_0 + c * kKPL;
+            const int lplane = seg1 ? p.plane0_1 + (lc - p.nch0l) * kKPL : p.plane0_0 + lc * kKPL;
+            const int plane = X3 ? 2 * lplane + ((c % 3) == 1 ? 4 : 0) : lplane;   // X3: hi, lo, hi again
             tma_load_4d(dst + (size_t)u * unit_bytes, tmap, &ctrl->full[s], x0 * 8, y0 + (C::ROWSPLIT ? sub : 0), plane, b);
             if (!p.resident) {
               const size_t woff = ((size_t)(nh * nchunks + c) * C::TAPS_C + (C::ROWSPLIT ? sub * KS : 0)) * C::W_TAP;
@@ -316,17 +340,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const bool valid = (tx < C::TW) && (y < yend) && (x < p.W);
       // operands of the epilogue that do not depend on the accumulators are fetched BEFORE waiting for
       // them, so their global-load latency overlaps the MMAs: the residual tile (RDN.py:165, :219) ...
-      uint4 rbuf[(EPI == BIN_EPI_P8 && !SX) ? (NT / 8) : 1];
+      uint4 rbuf[(EPI == BIN_EPI_P8 && !SX) ? (X3 ? 2 : 1) * (NT / 8) : 1];
       if constexpr (EPI == BIN_EPI_P8 && !SX) {
         if (p.res != nullptr) {
 #pragma unroll
           for (int k = 0; k < NT / 8; ++k) {
-            const size_t off = ((((size_t)b * p.res_planes + p.res_plane0 + (nh * NT) / 8 + k) * p.H + y) * p.W + x) * 8;
-            rbuf[k] = (valid && (nh * NT) / 8 + k < p.store_planes) ? *reinterpret_cast<const uint4*>(p.res + off)
-                                                                   : make_uint4(0, 0, 0, 0);
+            const int lp = p.res_plane0 + (nh * NT) / 8 + k;
+            const bool ok = valid && (nh * NT) / 8 + k < p.store_planes;
+            const size_t off = ((((size_t)b * p.res_planes + (X3 ? x3_plane(lp) : lp)) * p.H + y) * p.W + x) * 8;
+            rbuf[k] = ok ? *reinterpret_cast<const uint4*>(p.res + off) : make_uint4(0, 0, 0, 0);
+            if constexpr (X3)
+              rbuf[NT / 8 + k] = ok ? *reinterpret_cast<const uint4*>(p.res + off + (size_t)4 * p.H * p.W * 8) : make_uint4(0, 0, 0, 0);
           }
         }
       }
+      constexpr float kAcc = X3 ? (1.f / 256.f) : 1.f;      // X3 weights are packed scaled by 2^8
       if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 0);
       mbar_wait(&ctrl->tmem_full[as], aph);
       if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 1);
@@ -347,14 +375,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             for (int i = 0; i < 16; ++i) {
               const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), 1);
               const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 2);
-              f[i] = ((__uint_as_float(v0[i]) + b1) + b2) + sbias[n0 + i];
+              f[i] = ((__uint_as_float(v0[i]) + b1) + b2) * kAcc + sbias[n0 + i];
             }
           } else {
             uint32_t v[16];
             tmem_ld16(taddr + n0, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bsrc[nh * NT + n0 + i];
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * kAcc + bsrc[nh * NT + n0 + i];
           }
           if (valid) {
             if (p.relu) {
@@ -373,17 +401,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                   f[h * 8 + 2 * i] += g.x;
                   f[h * 8 + 2 * i + 1] += g.y;
                 }
+                if constexpr (X3 && !SX) {
+                  const uint4 r2 = rbuf[NT / 8 + n0 / 8 + h];
+                  const uint32_t rl[4] = {r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 g = unpack_h2(rl[i]);
+                    f[h * 8 + 2 * i] += g.x;
+                    f[h * 8 + 2 * i + 1] += g.y;
+                  }
+                }
               }
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              uint4 o;
-              o.x = pack_h2(f[h * 8 + 0], f[h * 8 + 1]);
-              o.y = pack_h2(f[h * 8 + 2], f[h * 8 + 3]);
-              o.z = pack_h2(f[h * 8 + 4], f[h * 8 + 5]);
-              o.w = pack_h2(f[h * 8 + 6], f[h * 8 + 7]);
-              const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + cpl + h) * p.H + y) * p.W + x) * 8;
-              if (cpl + h < p.store_planes) *reinterpret_cast<uint4*>(p.out + off) = o;
+              if constexpr (X3) {
+                const size_t off = ((((size_t)b * p.out_planes + x3_plane(p.out_plane0 + cpl + h)) * p.H + y) * p.W + x) * 8;
+                if (cpl + h < p.store_planes) split_store(p.out + off, p.out + off + (size_t)4 * p.H * p.W * 8, f + h * 8);
+              } else {
+                uint4 o;
+                o.x = pack_h2(f[h * 8 + 0], f[h * 8 + 1]);
+                o.y = pack_h2(f[h * 8 + 2], f[h * 8 + 3]);
+                o.z = pack_h2(f[h * 8 + 4], f[h * 8 + 5]);
+                o.w = pack_h2(f[h * 8 + 6], f[h * 8 + 7]);
+                const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + cpl + h) * p.H + y) * p.W + x) * 8;
+                if (cpl + h < p.store_planes) *reinterpret_cast<uint4*>(p.out + off) = o;
+              }
             }
           }
         }
@@ -399,21 +442,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             float f[32];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              f[i] = __uint_as_float(v0[i]) + sbias[nh * NT + n0 + i];
-              f[16 + i] = __uint_as_float(v1[i]) + sbias[nh * NT + n0 + 16 + i];
+              f[i] = __uint_as_float(v0[i]) * kAcc + sbias[nh * NT + n0 + i];
+              f[16 + i] = __uint_as_float(v1[i]) * kAcc + sbias[nh * NT + n0 + 16 + i];
             }
             const int opl = (nh * NT + n0) >> 5;   // output plane (8 channels = 32 conv channels)
             const int H2 = 2 * p.H, W2 = 2 * p.W;
 #pragma unroll
             for (int ij = 0; ij < 4; ++ij) {
-              uint4 o;
-              o.x = pack_h2(f[0 * 4 + ij], f[1 * 4 + ij]);
-              o.y = pack_h2(f[2 * 4 + ij], f[3 * 4 + ij]);
-              o.z = pack_h2(f[4 * 4 + ij], f[5 * 4 + ij]);
-              o.w = pack_h2(f[6 * 4 + ij], f[7 * 4 + ij]);
               const int yy = 2 * y + (ij >> 1), xx = 2 * x + (ij & 1);
-              const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + opl) * H2 + yy) * W2 + xx) * 8;
-              *reinterpret_cast<uint4*>(p.out + off) = o;
+              if constexpr (X3) {
+                float g8[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) g8[cc] = f[cc * 4 + ij];
+                const size_t off = ((((size_t)b * p.out_planes + x3_plane(p.out_plane0 + opl)) * H2 + yy) * W2 + xx) * 8;
+                split_store(p.out + off, p.out + off + (size_t)4 * H2 * W2 * 8, g8);
+              } else {
+                uint4 o;
+                o.x = pack_h2(f[0 * 4 + ij], f[1 * 4 + ij]);
+                o.y = pack_h2(f[2 * 4 + ij], f[3 * 4 + ij]);
+                o.z = pack_h2(f[4 * 4 + ij], f[5 * 4 + ij]);
+                o.w = pack_h2(f[6 * 4 + ij], f[7 * 4 + ij]);
+                const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + opl) * H2 + yy) * W2 + xx) * 8;
+                *reinterpret_cast<uint4*>(p.out + off) = o;
+              }
             }
           }
         }
@@ -429,14 +480,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           for (int c = 0; c < 3; ++c) {
             const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[c]), 1);
             const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c]), 2);
-            cv[c] = (__uint_as_float(v0[c]) + b1) + b2;
+            cv[c] = ((__uint_as_float(v0[c]) + b1) + b2) * kAcc;
           }
         } else {
           uint32_t v[16];
           tmem_ld16(taddr, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 3; ++c) cv[c] = __uint_as_float(v[c]);
+          for (int c = 0; c < 3; ++c) cv[c] = __uint_as_float(v[c]) * kAcc;
         }
         if (valid) {
           const int call = b / p.fr.Bc, bb = b % p.fr.Bc;
@@ -526,7 +577,7 @@ static int num_sms() {
   return n;
 }
 
-template <int NT, int KS, int EPI, bool SX>
+template <int NT, int KS, int EPI, bool SX, bool X3>
 static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
   using C = ConvCfg<NT, KS, SX>;
   ConvParams p;
@@ -537,8 +588,9 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
     if (a.in1.H != H || a.in1.W != W || a.in1.B != B) return fail(BIN_ERR_ARG, "in1 geometry differs from in0");
     BIN_TRY(make_p8_tmap(&p.tmap1, a.in1, C::ROWS));
   }
-  p.plane0_0 = a.in0_plane0; p.nch0 = a.in0_planes / kKPL;
-  p.plane0_1 = a.in1_plane0; p.nch1 = a.in1_planes / kKPL;
+  // X3: plane indices are LOGICAL (the tensors hold 2x the planes: hi/lo groups of 4), K has 3 chunks per logical chunk
+  p.plane0_0 = a.in0_plane0; p.nch0l = a.in0_planes / kKPL; p.nch0 = (X3 ? 3 : 1) * p.nch0l;
+  p.plane0_1 = a.in1_plane0; p.nch1 = (X3 ? 3 : 1) * (a.in1_planes / kKPL);
   p.w = reinterpret_cast<const __half*>(a.w_packed);
   p.bias = a.bias;
   p.H = H; p.W = W; p.Btot = B;
@@ -583,7 +635,7 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
     BIN_CUDA_OK(cudaMemsetAsync(g_dbg, 0, 3 * 4096 * sizeof(long long), s));
     p.dbg = g_dbg;
   }
-  auto kern = conv_igemm_kernel<NT, KS, EPI, SX>;
+  auto kern = conv_igemm_kernel<NT, KS, EPI, SX, X3>;
   static bool attr_done = false;   // per instantiation; idempotent, so a benign race at worst
   if (!attr_done) {
     BIN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
@@ -606,37 +658,45 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
   return BIN_OK;
 }
 
-int launch_conv(const bin_conv_args_t& a, cudaStream_t s) {
+template <bool X3>
+static int launch_conv_t(const bin_conv_args_t& a, cudaStream_t s) {
+  constexpr int f = X3 ? 2 : 1;      // X3 tensors hold hi+lo: twice the planes of their logical channel count
   if (a.in0_planes % kKPL || a.in1_planes % kKPL || a.in0_planes <= 0)
     return fail(BIN_ERR_ARG, "input plane counts must be positive multiples of 4 (32 channels)");
-  if (a.in0_plane0 + a.in0_planes > a.in0.planes || (a.in1_planes > 0 && a.in1_plane0 + a.in1_planes > a.in1.planes))
+  if (X3 && ((a.in0_plane0 | a.in1_plane0 | a.out_plane0 | a.res_plane0) & 3))
+    return fail(BIN_ERR_ARG, "x3 mode: plane offsets must be multiples of 4");
+  if (f * (a.in0_plane0 + a.in0_planes) > a.in0.planes || (a.in1_planes > 0 && f * (a.in1_plane0 + a.in1_planes) > a.in1.planes))
     return fail(BIN_ERR_ARG, "input plane range exceeds tensor");
   if (a.epilogue == BIN_EPI_P8) {
     const int nstore = a.store_planes > 0 ? a.store_planes : a.cout_pad / 8;
     if (a.out.H != a.in0.H || a.out.W != a.in0.W || a.out.B != a.in0.B || nstore > a.cout_pad / 8 ||
-        a.out_plane0 + nstore > a.out.planes)
+        f * (a.out_plane0 + nstore) > a.out.planes + (X3 ? 4 : 0))
       return fail(BIN_ERR_ARG, "output tensor geometry mismatch");
     if (a.res.ptr && (a.res.H != a.in0.H || a.res.W != a.in0.W || a.res.B != a.in0.B ||
-                      a.res_plane0 + nstore > a.res.planes))
+                      f * (a.res_plane0 + nstore) > a.res.planes + (X3 ? 4 : 0)))
       return fail(BIN_ERR_ARG, "residual tensor geometry mismatch");
-    if (a.ksize == 3 && a.cout_pad == 32 && a.variant == 0) return launch_inst<32, 3, BIN_EPI_P8, true>(a, s);
-    if (a.ksize == 3 && a.cout_pad == 32 && a.variant == 1) return launch_inst<32, 3, BIN_EPI_P8, false>(a, s);
-    if (a.ksize == 3 && a.cout_pad % 96 == 0) return launch_inst<96, 3, BIN_EPI_P8, false>(a, s);
-    if (a.ksize == 5 && a.cout_pad == 96) return launch_inst<96, 5, BIN_EPI_P8, false>(a, s);
-    if (a.ksize == 1 && a.cout_pad % 96 == 0) return launch_inst<96, 1, BIN_EPI_P8, false>(a, s);
+    if (a.ksize == 3 && a.cout_pad == 32 && a.variant == 0) return launch_inst<32, 3, BIN_EPI_P8, true, X3>(a, s);
+    if (a.ksize == 3 && a.cout_pad == 32 && a.variant == 1 && !X3) return launch_inst<32, 3, BIN_EPI_P8, false, false>(a, s);
+    if (a.ksize == 3 && a.cout_pad % 96 == 0) return launch_inst<96, 3, BIN_EPI_P8, false, X3>(a, s);
+    if (a.ksize == 5 && a.cout_pad == 96) return launch_inst<96, 5, BIN_EPI_P8, false, X3>(a, s);
+    if (a.ksize == 1 && a.cout_pad % 96 == 0) return launch_inst<96, 1, BIN_EPI_P8, false, X3>(a, s);
   } else if (a.epilogue == BIN_EPI_PIXSHUF) {
     if (a.out.H != 2 * a.in0.H || a.out.W != 2 * a.in0.W || a.out.B != a.in0.B ||
-        a.out_plane0 + a.cout_pad / 32 > a.out.planes)
+        f * (a.out_plane0 + a.cout_pad / 32) > a.out.planes)
       return fail(BIN_ERR_ARG, "pixel-shuffle output geometry mismatch");
-    if (a.ksize == 3 && a.cout_pad == 256) return launch_inst<128, 3, BIN_EPI_PIXSHUF, false>(a, s);
+    if (a.ksize == 3 && a.cout_pad == 256) return launch_inst<128, 3, BIN_EPI_PIXSHUF, false, X3>(a, s);
   } else if (a.epilogue == BIN_EPI_FINAL) {
     if (a.fr.ncalls < 1 || a.fr.ncalls > BIN_MAX_CALLS || a.fr.nframes < 1 || a.fr.nframes > BIN_MAX_FRAMES ||
         a.fr.ncalls * a.fr.Bc != a.in0.B)
       return fail(BIN_ERR_ARG, "frame table does not match the batch");
-    if (a.ksize == 3 && a.cout_pad == 16 && a.variant == 0) return launch_inst<16, 3, BIN_EPI_FINAL, true>(a, s);
-    if (a.ksize == 3 && a.cout_pad == 16 && a.variant == 1) return launch_inst<16, 3, BIN_EPI_FINAL, false>(a, s);
+    if (a.ksize == 3 && a.cout_pad == 16 && a.variant == 0) return launch_inst<16, 3, BIN_EPI_FINAL, true, X3>(a, s);
+    if (a.ksize == 3 && a.cout_pad == 16 && a.variant == 1 && !X3) return launch_inst<16, 3, BIN_EPI_FINAL, false, false>(a, s);
   }
-  return fail(BIN_ERR_UNSUPPORTED, "no kernel instantiation for this conv (ksize/cout_pad/epilogue)");
+  return fail(BIN_ERR_UNSUPPORTED, "no kernel instantiation for this conv (ksize/cout_pad/epilogue/precision)");
+}
+
+int launch_conv(const bin_conv_args_t& a, cudaStream_t s) {
+  return a.x3 ? launch_conv_t<true>(a, s) : launch_conv_t<false>(a, s);
 }
 
 }  // namespace binb

@@ -38,7 +38,8 @@ constexpr int kMaxResidentChunks = 8;
 
 struct alignas(64) ConvParams {
   CUtensorMap tmap0, tmap1;
-  int plane0_0, nch0, plane0_1, nch1;  // segment start plane / number of 32-channel chunks
+  int plane0_0, nch0, plane0_1, nch1;  // segment start plane / number of K chunks (X3: 3 per logical chunk)
+  int nch0l;                           // logical 32-channel chunks of segment 0
   const __half* w;
   const float* bias;
   int H, W, Btot;                      // conv resolution

@@ -22,7 +22,7 @@ import torch.nn.init as weight_init
 from . import _lib, ops
 from ._lib import BinB200Error, Net, check, lib
 
-__all__ = ["ConvLSTMCell", "pixel_reshuffle", "RDB_Conv", "RDB", "RDN_residual_interp_2_input",
+__all__ = ["set_precision", "ConvLSTMCell", "pixel_reshuffle", "RDB_Conv", "RDB", "RDN_residual_interp_2_input",
            "RDN_residual_interp_2_1_input", "RDN_residual_interp_4_1_input", "RDN_residual_interp_5_input",
            "RDN_residual_interp_5_input_ConvLSTM_L", "bin_stage4_lstm"]
 
@@ -166,9 +166,23 @@ class _Backbone(nn.Module):
         assert len(ps) == 2 * _lib.BIN_BACKBONE_NCONV
         return ps
 
-    def packed_blob(self) -> torch.Tensor:
+    def packed_blob(self, prec: int = 0) -> torch.Tensor:
+        """Packed weights for BIN_PREC_F16 (0) or BIN_PREC_F32X3 (1), cached per parameter version."""
         ps = self._conv_params()
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = (prec,) + tuple((p.data_ptr(), p._version) for p in ps)
+        if prec:
+            cached = self.__dict__.get("_packed_x3")
+            if cached is None or cached[0] != key:
+                dev = ps[0].device
+                if dev.type != "cuda":
+                    raise BinB200Error("bin_b200: parameters must live on a CUDA device (call .to('cuda')); no CPU fallback")
+                with torch.cuda.device(dev):
+                    blob = torch.empty(lib().bin_backbone_packed_bytes_p(self.NFRAMES, prec), dtype=torch.uint8, device=dev)
+                    wp = (C.c_void_p * _lib.BIN_BACKBONE_NCONV)(*[p.data_ptr() for p in ps[0::2]])
+                    bp = (C.c_void_p * _lib.BIN_BACKBONE_NCONV)(*[p.data_ptr() for p in ps[1::2]])
+                    check(lib().bin_backbone_pack_p(self.NFRAMES, wp, bp, blob.data_ptr(), prec, _stream()))
+                self.__dict__["_packed_x3"] = cached = (key, blob)
+            return cached[1]
         if self._packed is None or key != self._packed_key:
             dev = ps[0].device
             if dev.type != "cuda":
@@ -196,10 +210,11 @@ class _Backbone(nn.Module):
         with torch.cuda.device(dev):
             out = torch.empty_like(frames[0])
             fr = ops.make_frames([frames], [out])
-            nbytes = lib().bin_backbone_workspace_bytes(self.NFRAMES, B, H, W)
+            prec = _prec_of(self)
+            nbytes = lib().bin_backbone_workspace_bytes_p(self.NFRAMES, B, H, W, prec)
             ws = _workspace(dev, nbytes)
-            check(lib().bin_backbone_fwd(self.NFRAMES, self.packed_blob().data_ptr(), C.byref(fr), H, W, ws.data_ptr(),
-                                         ws.numel(), _stream()))
+            check(lib().bin_backbone_fwd_p(self.NFRAMES, self.packed_blob(prec).data_ptr(), C.byref(fr), H, W, ws.data_ptr(),
+                                           ws.numel(), prec, _stream()))
         return out
 
 
@@ -225,6 +240,24 @@ class RDN_residual_interp_4_1_input(_Backbone):     # RDN.py:282-334
 
 
 _WS = {}
+PRECISIONS = {"fp16": 0, "fp32": 1}
+
+
+def _prec_of(module) -> int:
+    """`module.precision` = "fp16" (default: fp16 storage / fp32 accumulate, <=1e-3) or "fp32" (split-fp16 x3 mode,
+    <=1e-5, ~3x slower).  Set it on the top-level net with set_precision(); sub-modules inherit through the attribute."""
+    name = getattr(module, "precision", "fp16")
+    if name not in PRECISIONS:
+        raise BinB200Error(f"unknown precision {name!r}; use 'fp16' or 'fp32'")
+    return PRECISIONS[name]
+
+
+def set_precision(net: nn.Module, precision: str) -> nn.Module:
+    if precision not in PRECISIONS:
+        raise BinB200Error(f"unknown precision {precision!r}; use 'fp16' or 'fp32'")
+    for m in net.modules():
+        m.precision = precision
+    return net
 
 
 def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
@@ -286,10 +319,11 @@ def _batched(model: _Backbone, calls):
     with torch.cuda.device(dev):
         outs = [torch.empty_like(calls[0][0]) for _ in calls]
         fr = ops.make_frames(calls, outs)
-        nbytes = lib().bin_backbone_workspace_bytes(model.NFRAMES, B * len(calls), H, W)
+        prec = _prec_of(model)
+        nbytes = lib().bin_backbone_workspace_bytes_p(model.NFRAMES, B * len(calls), H, W, prec)
         ws = _workspace(dev, nbytes)
-        check(lib().bin_backbone_fwd(model.NFRAMES, model.packed_blob().data_ptr(), C.byref(fr), H, W, ws.data_ptr(),
-                                     ws.numel(), _stream()))
+        check(lib().bin_backbone_fwd_p(model.NFRAMES, model.packed_blob(prec).data_ptr(), C.byref(fr), H, W, ws.data_ptr(),
+                                       ws.numel(), prec, _stream()))
     return outs
 
 
@@ -312,11 +346,11 @@ class RDN_residual_interp_5_input_ConvLSTM_L(nn.Module):
         self.prev_state = None
         self.hidden_state = None
 
-    def _net(self) -> Net:
+    def _net(self, prec: int = 0) -> Net:
         net = Net()
         pyr = self.model
         for k, m in enumerate((pyr.model1_1, pyr.model2_1, pyr.model3_1, pyr.model4_1)):
-            net.blob[k] = m.packed_blob().data_ptr()
+            net.blob[k] = m.packed_blob(prec).data_ptr()
         for k, n in enumerate(_LSTM_NAMES):
             cell = getattr(self, n)
             net.lstm_w[k] = cell.Gates.weight.data_ptr()
@@ -341,18 +375,19 @@ class RDN_residual_interp_5_input_ConvLSTM_L(nn.Module):
 
     def _launch_window(self, frames, B, H, W, dev):
         outs = [torch.empty_like(frames[0]) for _ in range(14)]
-        net = self._net()
-        ws = _workspace(dev, lib().bin_window_workspace_bytes(B, H, W))
+        prec = _prec_of(self)
+        net = self._net(prec)
+        ws = _workspace(dev, lib().bin_window_workspace_bytes_p(B, H, W, prec))
         fp = (C.c_void_p * 6)(*[f.data_ptr() for f in frames])
         op = (C.c_void_p * 14)(*[o.data_ptr() for o in outs])
-        check(lib().bin_window_fwd(C.byref(net), fp, op, B, H, W, ws.data_ptr(), ws.numel(), _stream()))
+        check(lib().bin_window_fwd_p(C.byref(net), fp, op, B, H, W, ws.data_ptr(), ws.numel(), prec, _stream()))
         return outs
 
     def _forward_graphed(self, frames, B, H, W, dev):
         """The ~340 kernel launches of a window are captured once per (shape, weight version) into a
         CUDA graph and replayed: removes ~10 % of host launch overhead at 720p.  Inputs are copied
         into the graph's static buffers, outputs are returned as fresh tensors."""
-        key = (dev.index, B, H, W, tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        key = (dev.index, B, H, W, _prec_of(self), tuple((p.data_ptr(), p._version) for p in self.parameters()))
         ent = self.__dict__.get("_graph_entry")
         with torch.cuda.device(dev):
             if ent is None or ent["key"] != key:

@@ -79,6 +79,9 @@ int bin_pack_conv_weight(const float* w_oihw, int cout, int cin, int ksize, int 
 /* ---- the implicit-GEMM convolution (tcgen05) ------------------------------------------ */
 enum { BIN_EPI_P8 = 0, BIN_EPI_PIXSHUF = 1, BIN_EPI_FINAL = 2 };
 enum { BIN_CONV_DEFAULT = 0, BIN_CONV_PLAIN = 1 };
+/* Precision modes: fp16 storage / fp32 accumulate (<=1e-3 parity), or the split-fp16 "fp32-accurate" mode
+ * (x = hi + lo, 3 MMAs per product, <=1e-5 parity; ~3x slower -- a correctness mode, not the benchmarked one). */
+enum { BIN_PREC_F16 = 0, BIN_PREC_F32X3 = 1 };
 typedef struct {
   /* input channels = planes [in0_plane0, +in0_planes) of in0 followed by planes of in1
    * (dense concat without a copy: RDN.py:147 torch.cat((x,out),1)); plane counts multiples of 4. */
@@ -97,6 +100,10 @@ typedef struct {
   /* BIN_EPI_P8 only: number of output planes actually stored (0 = cout_pad/8); lets a conv whose Cout was
    * zero-padded up to a multiple of 96 (the data-gradient launches) write a narrower tensor. */
   int store_planes;
+  /* 1 = fp32-accurate split mode: tensors carry (hi, lo) fp16 pairs -- per 32-channel chunk 4 planes of hi then
+   * 4 planes of lo, so bin_act_t.planes is twice the logical plane count while every *_plane0 / *_planes field
+   * stays LOGICAL (multiples of 4); weights must have been packed with BIN_PREC_F32X3. */
+  int x3;
   /* BIN_EPI_P8: out planes [out_plane0, +cout_pad/8), optional residual (RDN.py:165, :219) */
   bin_act_t out; int out_plane0;
   bin_act_t res; int res_plane0; /* res.ptr = NULL -> none */
@@ -171,6 +178,18 @@ size_t bin_window_workspace_bytes(int B, int H, int W);
  * ConvLSTM calls of its 12. */
 int bin_window_fwd(const bin_net_t* net, const float* const* frames_host, float* const* outs_host, int B, int H,
                    int W, void* workspace, size_t workspace_bytes, bin_stream_t s);
+/* Precision-parameterised twins of the calls above (prec = BIN_PREC_F16 | BIN_PREC_F32X3).  In BIN_PREC_F32X3 the
+ * packed blob is 3x and the workspace 2x as large; results match the fp32 reference to <=1e-5. */
+size_t bin_backbone_packed_bytes_p(int nframes, int prec);
+int bin_backbone_pack_p(int nframes, const float* const* w_host, const float* const* b_host, void* blob, int prec,
+                        bin_stream_t s);
+size_t bin_backbone_workspace_bytes_p(int nframes, int Btot, int H, int W, int prec);
+int bin_backbone_fwd_p(int nframes, const void* blob, const bin_frames_t* fr, int H, int W, void* workspace,
+                       size_t workspace_bytes, int prec, bin_stream_t s);
+size_t bin_window_workspace_bytes_p(int B, int H, int W, int prec);
+int bin_window_fwd_p(const bin_net_t* net, const float* const* frames_host, float* const* outs_host, int B, int H,
+                     int W, void* workspace, size_t workspace_bytes, int prec, bin_stream_t s);
+
 /* BASELINE config 2a/3a: stages 1-3 on 4 frames -> 6 outputs [I2',I4',I6',I3',I5',I4'']. */
 int bin_pyramid3_fwd(const bin_net_t* net, const float* const* frames_host, float* const* outs_host, int B, int H,
                      int W, void* workspace, size_t workspace_bytes, bin_stream_t s);

@@ -192,3 +192,44 @@ def test_full_size_properties(net):
     for k in range(14):
         assert torch.isfinite(oab[k]).all()
         assert torch.equal(oab[k][0:1], oa[k]) and torch.equal(oab[k][1:2], ob[k]), k
+
+
+# ------------------------------------------------------------------ fp32-accurate mode (north_star: 1e-5 max-abs)
+TOL_FP32_MODE = 1e-5
+
+
+@pytest.fixture(scope="module")
+def net32():
+    from bin_b200 import rdn
+    m = rdn.bin_stage4_lstm()
+    m.load_state_dict(O.synth_state_dict(0), strict=True)
+    return rdn.set_precision(m.cuda().eval(), "fp32")
+
+
+@pytest.mark.parametrize("name,n", [("model1_1", 2), ("model2_1", 3), ("model3_1", 5)])
+def test_fp32_mode_backbone_golden(golden_dir, net32, name, n):
+    g = _load(golden_dir, f"backbone_{name}.npz")
+    fr = [f.cuda() for f in O.synth_frames(n, 2, 20, 36, seed=100 + n)]
+    with torch.no_grad():
+        y = getattr(net32.model, name)(*fr).cpu()
+    assert (y - g["out"]).abs().max().item() <= TOL_FP32_MODE
+
+
+@pytest.mark.parametrize("tag", ["window_a", "window_b"])
+def test_fp32_mode_window_golden(golden_dir, net32, tag):
+    g = _load(golden_dir, tag + ".npz")
+    B, H, W, smooth, seed, _ = [int(v) for v in g["meta"]]
+    fr = [f.cuda() for f in O.synth_frames(6, B, H, W, seed=seed, smooth=bool(smooth))]
+    with torch.no_grad():
+        outs = net32(*fr)
+    worst = max((o.cpu() - g[f"out{k}"]).abs().max().item() for k, o in enumerate(outs))
+    assert worst <= TOL_FP32_MODE, worst
+
+
+def test_fp32_mode_window_vs_oracle(net32, sd):
+    fr = O.synth_frames(6, 1, 46, 122, seed=1234, smooth=True)
+    ref = O.window_forward(fr, sd)
+    with torch.no_grad():
+        outs = net32(*[f.cuda() for f in fr])
+    worst = max((o.cpu() - r).abs().max().item() for o, r in zip(outs, ref))
+    assert worst <= TOL_FP32_MODE, worst
