@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             for (int u = 0; u < nu; ++u)
               if ((unit + u) % C::NSUB == 0) mbar_wait(&ctrl->wfull[(unit + u) / C::NSUB], 0);
           }
-          while (ctrl->issued < it) { }                     // stage it-1 fully issued by the other warp
+          while (ctrl->issued < it) __nanosleep(32);        // stage it-1 fully issued by the other warp (a tight
+                                                            // shared-memory spin would compete with the MMA operand fetch)
           if (Y == 0 && lane == 0) dbg_rec(p, 1, dbg_it, 1);
           tc_fence_after();
           const uint32_t st_base = smem_u32(stage0 + (size_t)s * stage_bytes);
@@ -361,71 +362,82 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + m * C::NMMA;
       if constexpr (EPI == BIN_EPI_P8) {
+        // TMEM loads are issued in batches (tcgen05.wait::ld waits for ALL outstanding loads, so one wait per
+        // 16 columns serialised a ~200-cycle round trip six times per tile and made the LFF epilogue the bottleneck)
+        constexpr int GRP = SX ? 32 : (NT % 48 == 0 ? 48 : (NT % 32 == 0 ? 32 : 16));   // output channels per batch
 #pragma unroll
-        for (int n0 = 0; n0 < NT; n0 += 16) {
-          float f[16];
-          if constexpr (SX) {
-            // out[p] = D[p][kx=0] + D[p+1][kx=1] + D[p+2][kx=2]; p+1, p+2 are lanes +1, +2 of this warp
-            uint32_t v0[16], v1[16], v2[16];
-            tmem_ld16(taddr + n0, v0);
-            tmem_ld16(taddr + NT + n0, v1);
-            tmem_ld16(taddr + 2 * NT + n0, v2);
-            tmem_ld_wait();
+        for (int g0 = 0; g0 < NT; g0 += GRP) {
+          uint32_t v[(SX ? 3 : 1) * GRP];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), 1);
-              const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 2);
-              f[i] = ((__uint_as_float(v0[i]) + b1) + b2) * kAcc + sbias[n0 + i];
+          for (int j = 0; j < GRP / 16; ++j) {
+            if constexpr (SX) {
+              tmem_ld16(taddr + g0 + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
+              tmem_ld16(taddr + NT + g0 + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[GRP + 16 * j]));
+              tmem_ld16(taddr + 2 * NT + g0 + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[2 * GRP + 16 * j]));
+            } else {
+              tmem_ld16(taddr + g0 + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
             }
-          } else {
-            uint32_t v[16];
-            tmem_ld16(taddr + n0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * kAcc + bsrc[nh * NT + n0 + i];
           }
-          if (valid) {
-            if (p.relu) {
+          tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+          for (int j = 0; j < GRP / 16; ++j) {
+            const int n0 = g0 + 16 * j;
+            float f[16];
+            if constexpr (SX) {
+              // out[p] = D[p][kx=0] + D[p+1][kx=1] + D[p+2][kx=2]; p+1, p+2 are lanes +1, +2 of this warp
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[GRP + 16 * j + i]), 1);
+                const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[2 * GRP + 16 * j + i]), 2);
+                f[i] = ((__uint_as_float(v[16 * j + i]) + b1) + b2) * kAcc + sbias[n0 + i];
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[16 * j + i]) * kAcc + bsrc[nh * NT + n0 + i];
             }
-            const int cpl = (nh * NT + n0) >> 3;   // channel plane of f[0]
-            if (!SX && p.res != nullptr) {
+            if (valid) {
+              if (p.relu) {
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint4 r = rbuf[SX ? 0 : n0 / 8 + h];
-                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+              }
+              const int cpl = (nh * NT + n0) >> 3;   // channel plane of f[0]
+              if (!SX && p.res != nullptr) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 g = unpack_h2(rr[i]);
-                  f[h * 8 + 2 * i] += g.x;
-                  f[h * 8 + 2 * i + 1] += g.y;
-                }
-                if constexpr (X3 && !SX) {
-                  const uint4 r2 = rbuf[NT / 8 + n0 / 8 + h];
-                  const uint32_t rl[4] = {r2.x, r2.y, r2.z, r2.w};
+                for (int h = 0; h < 2; ++h) {
+                  const uint4 r = rbuf[SX ? 0 : n0 / 8 + h];
+                  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
-                    const float2 g = unpack_h2(rl[i]);
+                    const float2 g = unpack_h2(rr[i]);
                     f[h * 8 + 2 * i] += g.x;
                     f[h * 8 + 2 * i + 1] += g.y;
                   }
+                  if constexpr (X3 && !SX) {
+                    const uint4 r2 = rbuf[NT / 8 + n0 / 8 + h];
+                    const uint32_t rl[4] = {r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      const float2 g = unpack_h2(rl[i]);
+                      f[h * 8 + 2 * i] += g.x;
+                      f[h * 8 + 2 * i + 1] += g.y;
+                    }
+                  }
                 }
               }
-            }
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if constexpr (X3) {
-                const size_t off = ((((size_t)b * p.out_planes + x3_plane(p.out_plane0 + cpl + h)) * p.H + y) * p.W + x) * 8;
-                if (cpl + h < p.store_planes) split_store(p.out + off, p.out + off + (size_t)4 * p.H * p.W * 8, f + h * 8);
-              } else {
-                uint4 o;
-                o.x = pack_h2(f[h * 8 + 0], f[h * 8 + 1]);
-                o.y = pack_h2(f[h * 8 + 2], f[h * 8 + 3]);
-                o.z = pack_h2(f[h * 8 + 4], f[h * 8 + 5]);
-                o.w = pack_h2(f[h * 8 + 6], f[h * 8 + 7]);
-                const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + cpl + h) * p.H + y) * p.W + x) * 8;
-                if (cpl + h < p.store_planes) *reinterpret_cast<uint4*>(p.out + off) = o;
+              for (int h = 0; h < 2; ++h) {
+                if constexpr (X3) {
+                  const size_t off = ((((size_t)b * p.out_planes + x3_plane(p.out_plane0 + cpl + h)) * p.H + y) * p.W + x) * 8;
+                  if (cpl + h < p.store_planes) split_store(p.out + off, p.out + off + (size_t)4 * p.H * p.W * 8, f + h * 8);
+                } else {
+                  uint4 o;
+                  o.x = pack_h2(f[h * 8 + 0], f[h * 8 + 1]);
+                  o.y = pack_h2(f[h * 8 + 2], f[h * 8 + 3]);
+                  o.z = pack_h2(f[h * 8 + 4], f[h * 8 + 5]);
+                  o.w = pack_h2(f[h * 8 + 6], f[h * 8 + 7]);
+                  const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + cpl + h) * p.H + y) * p.W + x) * 8;
+                  if (cpl + h < p.store_planes) *reinterpret_cast<uint4*>(p.out + off) = o;
+                }
               }
             }
           }

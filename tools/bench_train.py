@@ -11,7 +11,7 @@ from bin_b200 import rdn  # noqa: E402
 from oracle import bin_oracle as O  # noqa: E402
 
 B, H, W = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (8, 256, 256)
-steps, warm = 5, 2
+steps, warm = int(os.environ.get("BT_STEPS", 5)), int(os.environ.get("BT_WARM", 2))
 net = rdn.bin_stage4_lstm()
 net.load_state_dict(O.synth_state_dict(0), strict=True)
 net = net.cuda().train()
