@@ -54,8 +54,9 @@ _SIGS = {
     "bin_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bin_conv_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "bin_pack_conv_weight_t": (C.c_int, [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
+    "bin_conv_wgrad_workspace_bytes": (C.c_size_t, []),
     "bin_conv_wgrad": (C.c_int, [Act, C.c_int, C.c_int, Act, C.c_int, C.c_int, Act, C.c_int, C.c_int, C.c_int, C.c_int,
-                                C.c_void_p, C.c_void_p, C.c_void_p]),
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bin_convlstm_fwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 3 + [C.c_void_p]),
     "bin_convlstm_bwd": (C.c_int, [C.c_void_p] * 13 + [C.c_int] * 3 + [C.c_void_p]),
     "bin_backbone_packed_bytes": (C.c_size_t, [C.c_int]),

@@ -289,7 +289,8 @@ int launch_grad_out_to_p8(const bin_frames_t& dout, int H, int W, const bin_act_
 int launch_bias_grad(const bin_act_t& dy, int plane0, int C, const float* scale, float* db, cudaStream_t s);
 int launch_wgrad(const bin_act_t& x0, int x0_plane0, int x0_planes, const bin_act_t& x1, int x1_plane0, int x1_planes,
                  const bin_act_t& dy, int dy_plane0, int cout, int cin, int ks, const float* scale, float* dw,
-                 cudaStream_t s);
+                 float* partial_ws, cudaStream_t s);
+constexpr size_t kWgradPartialBytes = (size_t)148 * 128 * 512 * sizeof(float);   // per-CTA accumulator slabs
 
 struct TSpec {          // one data-gradient conv: output rows [row0,row0+nrows) of the forward conv's Cin axis
   int conv, row0, nrows, cout_pad_t, cin_pad_t, ks;
@@ -332,6 +333,7 @@ static BackboneLayoutT backbone_layout_t(int nframes) {
 
 struct GradWs {
   bin_act_t dout16, du, dup0, dt2, dt1, dcat, df2, dg, dx0;
+  float* wg_partial;
   size_t bytes;
 };
 static GradWs grad_ws(int nframes, int Btot, int H, int W, void* base) {
@@ -354,6 +356,8 @@ static GradWs grad_ws(int nframes, int Btot, int H, int W, void* base) {
   w.df2 = carve(12, h, wd);
   w.dg = carve(16, h, wd);
   w.dx0 = carve((int)align_up(12 * nframes, kKC) / 8, h, wd);
+  w.wg_partial = base ? (float*)((uint8_t*)base + off) : nullptr;
+  off = align_up(off + kWgradPartialBytes, 256);
   w.bytes = off;
   return w;
 }
@@ -403,7 +407,7 @@ static int run_backbone_bwd(int nframes, const void* blob_t, const bin_frames_t&
                    const bin_act_t& dy, int dyp) -> int {
     const ConvSpec& c = L.conv[idx];
     BIN_TRY(launch_bias_grad(dy, dyp, c.cout, scale, gparams + GP.b[idx], s));
-    return launch_wgrad(x0, x0p, x0n, x1, x1p, x1n, dy, dyp, c.cout, c.cin, c.ks, scale, gparams + GP.w[idx], s);
+    return launch_wgrad(x0, x0p, x0n, x1, x1p, x1n, dy, dyp, c.cout, c.cin, c.ks, scale, gparams + GP.w[idx], gw.wg_partial, s);
   };
   const bin_act_t none = {nullptr, 0, 0, 0, 0};
 
@@ -510,10 +514,12 @@ int bin_pack_conv_weight_t(const float* w_oihw, int cout, int cin, int ksize, in
                            int cin_pad_t, void* packed, bin_stream_t s) {
   return launch_pack_weight_t(w_oihw, cout, cin, ksize, row0, nrows, cout_pad_t, cin_pad_t, packed, (cudaStream_t)s);
 }
+size_t bin_conv_wgrad_workspace_bytes(void) { return kWgradPartialBytes; }
 int bin_conv_wgrad(bin_act_t x0, int x0_plane0, int x0_planes, bin_act_t x1, int x1_plane0, int x1_planes, bin_act_t dy,
-                   int dy_plane0, int cout, int cin, int ksize, const float* scale_dev, float* dw, bin_stream_t s) {
+                   int dy_plane0, int cout, int cin, int ksize, const float* scale_dev, float* dw, void* workspace,
+                   bin_stream_t s) {
   return launch_wgrad(x0, x0_plane0, x0_planes, x1, x1_plane0, x1_planes, dy, dy_plane0, cout, cin, ksize, scale_dev, dw,
-                      (cudaStream_t)s);
+                      (float*)workspace, (cudaStream_t)s);
 }
 int bin_conv_fwd(const bin_conv_args_t* a, bin_stream_t s) {
   if (!a) return fail(BIN_ERR_ARG, "conv: null args");

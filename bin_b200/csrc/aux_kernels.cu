@@ -780,11 +780,12 @@ int launch_convlstm_bwd(const float* x, const float* c_prev, const float* h_prev
 }
 int launch_wgrad_impl(const bin_act_t& x0, int x0_plane0, int x0_planes, const bin_act_t& x1, int x1_plane0, int x1_planes,
                       const bin_act_t& dy, int dy_plane0, int cout, int cin, int ks, const float* scale, float* dw,
-                      cudaStream_t s);
+                      float* partial_ws, cudaStream_t s);
 int launch_wgrad(const bin_act_t& x0, int x0_plane0, int x0_planes, const bin_act_t& x1, int x1_plane0, int x1_planes,
                  const bin_act_t& dy, int dy_plane0, int cout, int cin, int ks, const float* scale, float* dw,
-                 cudaStream_t s) {
-  return launch_wgrad_impl(x0, x0_plane0, x0_planes, x1, x1_plane0, x1_planes, dy, dy_plane0, cout, cin, ks, scale, dw, s);
+                 float* partial_ws, cudaStream_t s) {
+  return launch_wgrad_impl(x0, x0_plane0, x0_planes, x1, x1_plane0, x1_planes, dy, dy_plane0, cout, cin, ks, scale, dw,
+                           partial_ws, s);
 }
 int run_mma_bench(int n, int iters, int mode, float* cycles_host) {
   if (n < 16 || n > 256 || n % 16) return fail(BIN_ERR_ARG, "microbench: N must be a multiple of 16 in [16,256]");

@@ -37,6 +37,7 @@ struct alignas(64) WgradParams {
   int nstages;
   const float* scale;
   float* dw;
+  float* partial;                                   // [gridDim.x][ntaps][128][n] fp32 per-CTA partial sums
 };
 
 struct WgCtrl {
@@ -145,28 +146,26 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     if (elect_one()) umma_commit(&ctrl->done);
     __syncwarp();
   } else if (warp >= 4) {
-    // ------------------------------------------------ flush: TMEM -> fp32 atomics into dW (OIHW)
+    // ------------------------------------------------ flush: TMEM -> this CTA's slab of the partial-sum workspace
+    // (plain 16-byte stores; 36.8 K fp32 atomics per CTA were issue-bound at ~1 lane/clk and took 4x the MMA time;
+    //  wgrad_reduce_kernel sums the slabs afterwards)
     mbar_wait(&ctrl->done, 0);
     tc_fence_after();
     const int q = warp & 3;
-    const int ci = p.ci_tile_plane0 * 8 + q * 32 + lane;        // this thread's input channel (accumulator row)
-    const float inv = 1.f / p.scale[0];
-    const int kk = p.ks * p.ks;
+    const int row = q * 32 + lane;                               // accumulator row = input channel within the tile
     const bool has_tiles = (int)blockIdx.x < p.ntiles;
+    float* slab = p.partial + (size_t)blockIdx.x * p.ntaps * 128 * p.n;
     for (int tp = 0; tp < p.ntaps; ++tp) {
       for (int n0 = 0; n0 < p.n; n0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tp * p.n + n0, v);
         tmem_ld_wait();
-        if (has_tiles && ci < p.cin) {
+        float4* dst = reinterpret_cast<float4*>(slab + ((size_t)tp * 128 + row) * p.n + n0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int col = n0 + i;
-            const int co = p.sx ? (col & 31) : col;
-            const int tap = p.sx ? tp * 3 + (col >> 5) : p.tap0 + tp;
-            if (co < p.cout) atomicAdd(p.dw + ((size_t)co * p.cin + ci) * kk + tap, __uint_as_float(v[i]) * inv);
-          }
-        }
+        for (int i = 0; i < 4; ++i)
+          dst[i] = has_tiles ? make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                           __uint_as_float(v[4 * i + 3]))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   }
@@ -175,12 +174,31 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// dW[co][ci][tap] += (1/scale) * sum over CTAs of partial[cta][tp][ci - ci0][col]   (col = co, or kx*32+co in SX mode)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nctas, int ntaps, int n, int sx, int tap0,
+                                    int ci0, int cout, int cin, int kk, const float* __restrict__ scale,
+                                    float* __restrict__ dw) {
+  const int total = ntaps * 128 * n;
+  const float inv = 1.f / scale[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int col = i % n, row = (i / n) % 128, tp = i / (n * 128);
+    const int ci = ci0 + row;
+    const int co = sx ? (col & 31) : col;
+    const int tap = sx ? tp * 3 + (col >> 5) : tap0 + tp;
+    if (ci >= cin || co >= cout) continue;
+    float acc = 0.f;
+    for (int c = 0; c < nctas; ++c) acc += partial[(size_t)c * total + i];
+    dw[((size_t)co * cin + ci) * kk + tap] += acc * inv;
+  }
+}
+
 int make_p8_tmap_box(CUtensorMap* m, const bin_act_t& t, int box_px, int box_rows, int box_planes);
 
 int launch_wgrad_impl(const bin_act_t& x0, int x0_plane0, int x0_planes, const bin_act_t& x1, int x1_plane0, int x1_planes,
                       const bin_act_t& dy, int dy_plane0, int cout, int cin, int ks, const float* scale, float* dw,
-                      cudaStream_t s) {
+                      float* partial_ws, cudaStream_t s) {
   if (ks != 1 && ks != 3 && ks != 5) return fail(BIN_ERR_ARG, "wgrad: ksize must be 1, 3 or 5");
+  if (!partial_ws) return fail(BIN_ERR_ARG, "wgrad: partial-sum workspace missing");
   int n = (cout + 15) / 16 * 16;
   if (n > 256) return fail(BIN_ERR_UNSUPPORTED, "wgrad: Cout > 256");
   if (dy_plane0 + n / 8 > dy.planes) return fail(BIN_ERR_ARG, "wgrad: dY plane range exceeds tensor");   // (before SX widening)
@@ -198,7 +216,7 @@ int launch_wgrad_impl(const bin_act_t& x0, int x0_plane0, int x0_planes, const b
   p.B = x0.B; p.H = x0.H; p.W = x0.W;
   p.tiles_x = (p.W + kWgTW - 1) / kWgTW; p.tiles_y = (p.H + kWgTH - 1) / kWgTH;
   p.ntiles = p.B * p.tiles_x * p.tiles_y;
-  p.scale = scale; p.dw = dw;
+  p.scale = scale; p.dw = dw; p.partial = partial_ws;
   const int x_bytes = 16 * p.rows * p.pw * 16, y_bytes = (n / 8) * kWgTH * kWgTW * 16;
   int S = (kSmemMax - 1024) / (x_bytes + y_bytes);
   if (S > 3) S = 3;
@@ -221,6 +239,10 @@ int launch_wgrad_impl(const bin_act_t& x0, int x0_plane0, int x0_planes, const b
       p.tap0 = t0;
       p.ntaps = kk - t0 < taps_per_group ? kk - t0 : taps_per_group;
       wgrad_kernel<<<grid, 256, smem_bytes, s>>>(p);
+      BIN_CUDA_OK(cudaGetLastError());
+      const int total = p.ntaps * 128 * n;
+      wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(partial_ws, grid, p.ntaps, n, p.sx, t0, cp * 8, cout, cin, ks * ks,
+                                                            scale, dw);
       BIN_CUDA_OK(cudaGetLastError());
     }
   }

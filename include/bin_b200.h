@@ -120,9 +120,12 @@ int bin_conv_fwd(const bin_conv_args_t* a, bin_stream_t s);
 int bin_pack_conv_weight_t(const float* w_oihw, int cout, int cin, int ksize, int row0, int nrows, int cout_pad_t,
                            int cin_pad_t, void* packed, bin_stream_t s);
 /* Weight gradient of one conv: dw (cout,cin,k,k fp32 OIHW) += (1/ *scale_dev) * sum_px dY[px][co] X[px+tap][ci];
- * X = planes of x0 followed by planes of x1 (like bin_conv_args_t), dY = planes [dy_plane0, +ceil(cout/8)). */
+ * X = planes of x0 followed by planes of x1 (like bin_conv_args_t), dY = planes [dy_plane0, +ceil(cout/8)).
+ * workspace: bin_conv_wgrad_workspace_bytes() bytes (per-CTA partial sums, reduced by a second kernel). */
+size_t bin_conv_wgrad_workspace_bytes(void);
 int bin_conv_wgrad(bin_act_t x0, int x0_plane0, int x0_planes, bin_act_t x1, int x1_plane0, int x1_planes, bin_act_t dy,
-                   int dy_plane0, int cout, int cin, int ksize, const float* scale_dev, float* dw, bin_stream_t s);
+                   int dy_plane0, int cout, int cin, int ksize, const float* scale_dev, float* dw, void* workspace,
+                   bin_stream_t s);
 
 /* ---- ConvLSTMCell.forward, RDN.py:50-95 ------------------------------------------------ */
 /* x,(c_prev,h_prev): (B,3,H,W) fp32; c_prev/h_prev NULL = zeros (RDN.py:57-68);

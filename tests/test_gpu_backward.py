@@ -167,8 +167,9 @@ def test_single_conv_dgrad_wgrad_exact(cin, cout, k, split):
         x1t = ops.nchw_to_p8(x.detach()[:, split:].contiguous())
         x0p, x1p = split // 8, (cin - split) // 8
         a1 = ops.act_view(x1t)
+    wsp = torch.empty(lib().bin_conv_wgrad_workspace_bytes(), dtype=torch.uint8, device=dev)
     check(lib().bin_conv_wgrad(ops.act_view(x0), 0, x0p, a1, 0, x1p, ops.act_view(dys), 0, cout, cin, k,
-                               scale.data_ptr(), dw.data_ptr(), st))
+                               scale.data_ptr(), dw.data_ptr(), wsp.data_ptr(), st))
     torch.cuda.synchronize()
     assert (dw - gw_ref).abs().max().item() <= 1e-4 * gw_ref.abs().max().item()
 
