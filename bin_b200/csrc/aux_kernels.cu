@@ -638,6 +638,62 @@ __global__ void __launch_bounds__(128, 1) mma_pattern_kernel(int tiles, int vary
   }
 }
 
+// 2-CTA (cta_group::2) issue-rate probe: a CTA pair shares one 256 x N x 16 MMA (A: 128 rows from each CTA's smem,
+// B: N/2 rows from each), issued by the leader CTA.  Measures cycles per MMA to size the benefit for round 2.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma2_bench_kernel(int n, int iters, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tb = tmem_base_s;
+  if (rank == 0 && threadIdx.x < 32) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 48 * 1024);
+    const uint64_t ad0 = umma_desc_kmajor_noswz(a0, 320 * 16, 128);
+    const uint64_t bd0 = umma_desc_kmajor_noswz(b0, (uint32_t)(n / 2) * 16, 128);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 8) {
+      if (elect_one()) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tb + (uint32_t)(u % 2) * (uint32_t)n),
+              "l"(ad0 + (uint64_t)u), "l"(bd0), "r"(idesc), "r"(1u)
+              : "memory");
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one())
+      asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x / 2] = t1 - t0;
+  }
+  tc_fence_before();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ launch wrappers
 static inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
@@ -792,7 +848,11 @@ int run_mma_bench(int n, int iters, int mode, float* cycles_host) {
   long long* d = nullptr;
   const int grid = 148;
   BIN_CUDA_OK(cudaMalloc(&d, grid * sizeof(long long)));
-  if (mode & 0x1000) {                       // conv-pattern replay: n = ignored, iters = tiles
+  BIN_CUDA_OK(cudaMemset(d, 0, grid * sizeof(long long)));
+  if (mode & 0x2000) {                       // 2-CTA pair probe
+    BIN_CUDA_OK(cudaFuncSetAttribute(mma2_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    mma2_bench_kernel<<<grid, 128, 96 * 1024>>>(n, iters, d);
+  } else if (mode & 0x1000) {                // conv-pattern replay: n = ignored, iters = tiles
     BIN_CUDA_OK(cudaFuncSetAttribute(mma_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     mma_pattern_kernel<<<grid, 128, 160 * 1024>>>(iters, mode & 7, d);
     iters *= 36;

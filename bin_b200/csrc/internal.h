@@ -11,7 +11,6 @@
 namespace binb {
 
 // ------------------------------------------------------------------ errors
-void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 #define BIN_CUDA_OK(expr)                                                                          \
   do {                                                                                             \

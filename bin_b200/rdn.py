@@ -36,12 +36,6 @@ def _graphs_enabled() -> bool:
     return os.environ.get("BIN_B200_GRAPH", "1") != "0"
 
 
-def _no_grad_path(*tensors: torch.Tensor) -> None:
-    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
-        from . import autograd  # noqa: F401  (backward lives in bin_b200.autograd)
-        raise BinB200Error("internal: grad-enabled call reached the inference path")
-
-
 def _check_frames(frames: Sequence[torch.Tensor]) -> Tuple[int, int, int]:
     f0 = frames[0]
     if not f0.is_cuda:
@@ -87,7 +81,6 @@ def pixel_reshuffle(input, upscale_factor):
         raise BinB200Error("pixel_reshuffle: only upscale_factor=2 is on the BIN hot path")
     x = input.contiguous()
     B, Cc, H, W = x.shape
-    planes = (Cc * 4 + 31) // 32 * 4
     # one "frame" per 3 channels so that the packer's (f*3+rgb)*4+dy*2+dx order equals c*4+i*2+j
     if Cc % 3:
         raise BinB200Error("pixel_reshuffle: channel count must be a multiple of 3")

@@ -127,7 +127,18 @@ def case_sub(cin=128, k=3, cout=32):
     print(json.dumps(res))
 
 
+def case_mma2():
+    from bin_b200 import ops
+    res = {}
+    for n in (32, 64, 96, 128, 192, 256):
+        res[f"pair_M256_N{n}"] = round(ops.microbench_mma(n, 8192, 0x2000), 2)
+    for n in (96, 128, 256):
+        res[f"single_M128_N{n}"] = round(ops.microbench_mma(n, 8192, 2), 2)
+    print(json.dumps(res))
+
+
 CASES = {
+    "mma2": case_mma2,
     "mmapat": case_mmapat,
     "sub3": lambda: case_sub(128, 3, 32),
     "sub1": lambda: case_sub(224, 1, 96),
