@@ -85,6 +85,9 @@ _SIGS = {
                                    C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "bin_pyramid3_fwd": (C.c_int, [C.POINTER(Net), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "bin_pixel_loss_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "bin_pixel_loss_bwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
+                                    C.c_size_t, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "bin_tensor2img_u8": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
     "bin_u8_to_frame": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
     "bin_microbench_mma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),

@@ -352,6 +352,55 @@ __global__ void u8_to_frame_kernel(const uint8_t* __restrict__ src, int h, int w
   }
 }
 
+// ------------------------------------------------------------------ fused pixel loss
+// bin_model.get_loss (bin_model.py:395-425): loss = mean over pairs of cri_pix(a_k, b_k) with cri_pix = L1 sum
+// (bin_model.py:55), MSE sum (:57) or Charbonnier mean sqrt(d^2+eps) (loss.py:130-140).  One launch reduces all
+// pairs (up to 17: 14 outputs vs GT + 3 cycle terms), one launch writes all gradients.
+struct LossPairs {
+  const float* a[BIN_MAX_LOSS_PAIRS];
+  const float* b[BIN_MAX_LOSS_PAIRS];
+  float* da[BIN_MAX_LOSS_PAIRS];
+  float* db[BIN_MAX_LOSS_PAIRS];
+  int npairs;
+};
+__device__ __forceinline__ float loss_term(float d, int kind, float eps) {
+  return kind == 0 ? fabsf(d) : (kind == 1 ? d * d : sqrtf(d * d + eps));
+}
+__global__ void pixel_loss_fwd_kernel(const __grid_constant__ LossPairs P, size_t n, int kind, float eps,
+                                      float* __restrict__ pair_loss) {
+  const int k = blockIdx.y;
+  const float* a = P.a[k];
+  const float* b = P.b[k];
+  float acc = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    acc += loss_term(a[i] - b[i], kind, eps);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += part[wv];
+    atomicAdd(pair_loss + k, kind == 2 ? s / (float)n : s);
+  }
+}
+// da_k = g * dterm/dd, db_k = -da_k, with g = upstream / npairs (and / n for the Charbonnier mean)
+__global__ void pixel_loss_bwd_kernel(const __grid_constant__ LossPairs P, size_t n, int kind, float eps,
+                                      const float* __restrict__ upstream) {
+  const int k = blockIdx.y;
+  const float* a = P.a[k];
+  const float* b = P.b[k];
+  float* da = P.da[k];
+  float* db = P.db[k];
+  const float g = upstream[0] / (float)P.npairs * (kind == 2 ? 1.f / (float)n : 1.f);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    const float t = kind == 0 ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : (kind == 1 ? 2.f * d : d / sqrtf(d * d + eps));
+    if (da) da[i] = g * t;
+    if (db) db[i] = -g * t;
+  }
+}
+
 // ------------------------------------------------------------------ ConvLSTMCell backward (fp32)
 // Pass 1 (per pixel): recompute the gates (RDN.py:74-82), write d(gate pre-activations) [B,12,H,W] and dc_prev.
 __global__ void convlstm_bwd_gates_kernel(const float* __restrict__ x, const float* __restrict__ c_prev,
@@ -817,6 +866,31 @@ int launch_u8_to_frame(const uint8_t* img, int h, int w, int pl, int pr, int pt,
   if (h < 1 || w < 1 || pl < 0 || pr < 0 || pt < 0 || pb < 0) return fail(BIN_ERR_ARG, "u8_to_frame: bad geometry");
   const int Hp = h + pt + pb, Wp = w + pl + pr;
   u8_to_frame_kernel<<<grid_for((size_t)Hp * Wp, 256), 256, 0, s>>>(img, h, w, pl, pt, Hp, Wp, out);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_pixel_loss_fwd(const float* const* a, const float* const* b, int npairs, size_t n, int kind, float eps,
+                          float* pair_loss, cudaStream_t s) {
+  if (npairs < 1 || npairs > BIN_MAX_LOSS_PAIRS || kind < 0 || kind > 2) return fail(BIN_ERR_ARG, "pixel_loss: bad pair count / kind");
+  LossPairs P;
+  memset(&P, 0, sizeof(P));
+  P.npairs = npairs;
+  for (int k = 0; k < npairs; ++k) { P.a[k] = a[k]; P.b[k] = b[k]; }
+  BIN_CUDA_OK(cudaMemsetAsync(pair_loss, 0, npairs * sizeof(float), s));
+  dim3 grid((unsigned)((n + 256 * 16 - 1) / (256 * 16) < 256 ? (n + 256 * 16 - 1) / (256 * 16) : 256), npairs);
+  pixel_loss_fwd_kernel<<<grid, 256, 0, s>>>(P, n, kind, eps, pair_loss);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_pixel_loss_bwd(const float* const* a, const float* const* b, float* const* da, float* const* db, int npairs,
+                          size_t n, int kind, float eps, const float* upstream, cudaStream_t s) {
+  if (npairs < 1 || npairs > BIN_MAX_LOSS_PAIRS || kind < 0 || kind > 2) return fail(BIN_ERR_ARG, "pixel_loss: bad pair count / kind");
+  LossPairs P;
+  memset(&P, 0, sizeof(P));
+  P.npairs = npairs;
+  for (int k = 0; k < npairs; ++k) { P.a[k] = a[k]; P.b[k] = b[k]; P.da[k] = da[k]; P.db[k] = db ? db[k] : nullptr; }
+  dim3 grid((unsigned)((n + 256 * 8 - 1) / (256 * 8) < 512 ? (n + 256 * 8 - 1) / (256 * 8) : 512), npairs);
+  pixel_loss_bwd_kernel<<<grid, 256, 0, s>>>(P, n, kind, eps, upstream);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
 }

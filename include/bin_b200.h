@@ -36,6 +36,7 @@ extern "C" {
 #define BIN_ABI_VERSION 1
 #define BIN_MAX_CALLS 6   /* same-weight backbone calls batched along N */
 #define BIN_MAX_FRAMES 5  /* frames per backbone call (2, 3 or 5) */
+#define BIN_MAX_LOSS_PAIRS 20 /* (prediction, target) pairs of one fused loss call */
 
 enum { BIN_OK = 0, BIN_ERR_ARG = 1, BIN_ERR_CUDA = 2, BIN_ERR_UNSUPPORTED = 3, BIN_ERR_WORKSPACE = 4 };
 
@@ -196,6 +197,17 @@ int bin_window_fwd_p(const bin_net_t* net, const float* const* frames_host, floa
 /* BASELINE config 2a/3a: stages 1-3 on 4 frames -> 6 outputs [I2',I4',I6',I3',I5',I4'']. */
 int bin_pyramid3_fwd(const bin_net_t* net, const float* const* frames_host, float* const* outs_host, int B, int H,
                      int W, void* workspace, size_t workspace_bytes, bin_stream_t s);
+
+/* ---- fused pixel loss: bin_model.get_loss, bin_model.py:395-425 ---------------------- */
+/* kind: 0 = nn.L1Loss(reduction='sum') (bin_model.py:55), 1 = nn.MSELoss(reduction='sum') (:57),
+ * 2 = CharbonnierLoss mean sqrt(d^2+eps) (loss.py:130-140).  pair_loss[k] (device fp32[npairs]) = cri_pix(a_k, b_k);
+ * the caller's loss is their mean.  a_host/b_host: host arrays of npairs device pointers, n elements each. */
+enum { BIN_LOSS_L1_SUM = 0, BIN_LOSS_L2_SUM = 1, BIN_LOSS_CHARBONNIER_MEAN = 2 };
+int bin_pixel_loss_fwd(const float* const* a_host, const float* const* b_host, int npairs, size_t n, int kind, float eps,
+                       float* pair_loss, bin_stream_t s);
+/* da_k = (upstream/npairs) * d cri_pix / d a_k, db_k = -da_k (db_host or single entries may be NULL). */
+int bin_pixel_loss_bwd(const float* const* a_host, const float* const* b_host, float* const* da_host, float* const* db_host,
+                       int npairs, size_t n, int kind, float eps, const float* upstream, bin_stream_t s);
 
 /* ---- image boundary of the caller loop ------------------------------------ */
 /* utils/util.py:113-137 tensor2img + the crop of test.py:394-402 for ONE (3,Hs,Ws) fp32 RGB image:

@@ -253,6 +253,21 @@ def psnr_u8(a: Tensor, b: Tensor) -> float:
     return 20.0 * math.log10(255.0 / math.sqrt(mse))
 
 
+def get_loss_6v2(outs: Sequence[Tensor], gts: Sequence[Tensor], kind: str = "l1", eps: float = 1e-6):
+    """bin_model.get_loss(ret=1) for nframes == 6, version == 2 (bin_model.py:395-425) with cri_pix = L1 sum (:55),
+    MSE sum (:57) or CharbonnierLoss (loss.py:130-140).  Returns (loss, loss_list[:num])."""
+    def cri(x, y):
+        d = x - y
+        if kind == "l1":
+            return d.abs().sum()
+        if kind == "l2":
+            return (d * d).sum()
+        return torch.sqrt(d * d + eps).mean()
+    terms = [cri(o, g) for o, g in zip(outs, gts)]                                   # :400-402
+    terms += [cri(outs[1], outs[7]), cri(outs[5], outs[9]), cri(outs[2], outs[8])]   # :409-415
+    return sum(terms) / len(terms), terms[:len(outs)]                                # :416, :418
+
+
 def read_image_u8(img_bgr_u8):
     """test.py:44-56 read_image on an already decoded uint8 HWC BGR array -> (3,H,W) fp32 RGB in [0,1]."""
     import numpy as np

@@ -99,6 +99,25 @@ def main():
     t.view(-1)[:6] = torch.tensor([0.5 / 255, 1.5 / 255, 2.5 / 255, 254.5 / 255, 1.0, 0.0])
     save("tensor2img.npz", x=t.numpy(), out=RU.tensor2img(t.clone()))
 
+    # -- bin_model.get_loss (bin_model.py:395-425) called on a stand-in object with the reference's own criteria --------
+    import models.bin_model as BM
+    from models.loss import CharbonnierLoss
+
+    class _Stub:
+        pass
+    g = torch.Generator().manual_seed(3)
+    louts = [torch.rand((1, 3, 8, 10), generator=g) for _ in range(14)]
+    lgts = [torch.rand((1, 3, 8, 10), generator=g) for _ in range(14)]
+    stub = _Stub()
+    stub.Ft_p, stub.nframes, stub.version, stub.get_info = louts, 6, 2, (lambda mode=1: (14, lgts))
+    rec = {}
+    for name, cri in (("l1", torch.nn.L1Loss(reduction="sum")), ("l2", torch.nn.MSELoss(reduction="sum")), ("cb", CharbonnierLoss())):
+        stub.cri_pix = cri
+        loss, ll = BM.bin_model.get_loss(stub, ret=1)
+        rec[name] = loss.numpy()
+        rec[name + "_list"] = torch.stack(ll).numpy()
+    save("get_loss.npz", outs=torch.stack(louts).numpy(), gts=torch.stack(lgts).numpy(), **rec)
+
     # -- backward: d(sum_k <out_k, cot_k>)/d(frames, a few params) (config 3) ----------
     net.train()
     fr = [f.requires_grad_(True) for f in O.synth_frames(6, 1, 16, 16, seed=9)]

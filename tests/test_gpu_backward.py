@@ -191,3 +191,21 @@ def test_pyramid3_training_config3a(net):
         err = (frg[k].grad.cpu() - gref[k]).abs().max().item() / gref[k].abs().max().item()
         assert err <= 0.03, (k, err)
     assert net.model.model3_1.UPNet[2].weight.grad is not None and net.model.model4_1.UPNet[2].weight.grad is None
+
+
+@pytest.mark.parametrize("kind", ["l1", "l2", "cb"])
+def test_fused_pixel_loss_matches_get_loss(golden_dir, kind):
+    """bin_b200.loss.pixel_loss vs the reference's bin_model.get_loss (golden) and oracle autograd for the gradients."""
+    from bin_b200.loss import pixel_loss
+    g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, "get_loss.npz")).items()}
+    outs = [t.clone().cuda().requires_grad_(True) for t in g["outs"]]
+    gts = [t.clone().cuda() for t in g["gts"]]
+    loss, ll = pixel_loss(outs, gts, kind)
+    assert abs(loss.item() - g[kind].item()) <= 1e-5 * max(1.0, abs(g[kind].item()))
+    assert (torch.stack(ll).cpu() - g[kind + "_list"]).abs().max().item() <= 1e-4 * max(1.0, g[kind + "_list"].abs().max().item())
+    loss.backward()
+    ro = [t.clone().requires_grad_(True) for t in g["outs"]]
+    rl, _ = O.get_loss_6v2(ro, list(g["gts"]), kind)
+    rg = torch.autograd.grad(rl, ro)
+    for a, b in zip(outs, rg):
+        assert (a.grad.cpu() - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item())

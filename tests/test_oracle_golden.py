@@ -108,3 +108,11 @@ def test_window_grad(golden_dir, sd):
 def test_tensor2img(golden_dir):
     g = np.load(os.path.join(golden_dir, "tensor2img.npz"))
     assert np.array_equal(O.tensor2img_bgr_u8(torch.from_numpy(g["x"])), g["out"])
+
+
+@pytest.mark.parametrize("kind", ["l1", "l2", "cb"])
+def test_get_loss(golden_dir, kind):
+    g = _load(golden_dir, "get_loss.npz")
+    loss, ll = O.get_loss_6v2(list(g["outs"]), list(g["gts"]), kind)
+    assert abs(loss.item() - g[kind].item()) <= 1e-5 * max(1.0, abs(g[kind].item()))
+    assert (torch.stack(ll) - g[kind + "_list"]).abs().max().item() <= 1e-4 * max(1.0, g[kind + "_list"].abs().max().item())

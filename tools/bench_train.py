@@ -17,14 +17,14 @@ net.load_state_dict(O.synth_state_dict(0), strict=True)
 net = net.cuda().train()
 fr = [f.cuda() for f in O.synth_frames(6, B, H, W, seed=1234, smooth=True)]
 gt = [f.cuda() for f in O.synth_frames(14, B, H, W, seed=4321, smooth=True)]
-crit = torch.nn.L1Loss(reduction="sum")
-opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99))
+from bin_b200.loss import pixel_loss  # noqa: E402  (fused bin_model.get_loss: 14 GT terms + 3 cycle terms, L1 sum)
+opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99), fused=True)     # yml :52-55
 
 
 def step():
     opt.zero_grad(set_to_none=True)
     outs = net(*fr)
-    loss = sum(crit(o, g) for o, g in zip(outs, gt)) / 14.0
+    loss, _ = pixel_loss(outs, gt, "l1")
     loss.backward()
     return loss
 
@@ -42,7 +42,7 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 flops = 3 * 2.0 * 14_234_976 * B * H * W
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
-print(json.dumps({"config": f"train step fwd+bwd, 6-frame net, batch {B} x {H}x{W}, L1(sum)/14, Adam excluded from timing",
+print(json.dumps({"config": f"train step fwd+bwd, 6-frame net, batch {B} x {H}x{W}, get_loss(l1, 17 terms) fused, Adam excluded from timing",
                   "ms_per_step": round(ms, 2), "tflops_reference_as_executed(3xF_fwd)": round(flops / ms / 1e9, 1),
                   "frac_of_sustained_peak": round(flops / (ms * 1e-3) / 1e12 / peak, 4),
                   "loss_first_warmup_steps": losses, "loss_last": l.item(),
