@@ -15,7 +15,7 @@ os.makedirs(P, exist_ok=True)
 
 
 def short(name):
-    m = re.search(r"conv_igemm_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d)>", name)
+    m = re.search(r"conv_igemm_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d)(?:, (?:\(bool\))?\d)?>", name)
     if m:
         epi = {"0": "P8", "1": "PIXSHUF", "2": "FINAL"}[m.group(3)]
         return f"conv_igemm<NT={m.group(1)},KS={m.group(2)},{epi},SX={m.group(4)}>"
@@ -82,5 +82,7 @@ full("prof_rdb5.ncu-rep", "ncu --set full: RDB 5 of the stage-1 launch (5 batche
      "Command: `ncu --set full --clock-control none --import-source on -k regex:conv_igemm_kernel -s 357 -c 5 python tools/run_window.py 2`.\n"
      "Algorithmic bytes per launch: conv c reads 5*230400*(192+64c) B and writes 5*230400*64 B; LFF reads 5*230400*640 B, writes 5*230400*192 B.\n"
      "Algorithmic FLOPs per launch: 2*5*230400*(96+32c)*32*9 (conv c), 2*5*230400*224*96 (LFF).")
+full("prof_wgrad.ncu-rep", "ncu --set full: weight-gradient GEMM (tcgen05 MN-major) inside a training step, batch 4 x 256x256",
+     "Command: `BT_STEPS=1 BT_WARM=1 ncu --set full --clock-control none --import-source on -k regex:wgrad_kernel -s 300 -c 2 python tools/bench_train.py 4 256 256` (captured before the slab-reduce flush replaced the atomics).")
 full("prof_tail.ncu-rep", "ncu --set full: tail of the same stage: GFF.0, GFF.1, UPNet.0(+PixelShuffle), UPNet.2(+mean)",
      "Command: `ncu --set full --clock-control none --import-source on -k regex:conv_igemm_kernel -s 392 -c 4 python tools/run_window.py 2`.")
