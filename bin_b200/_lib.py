@@ -102,9 +102,15 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise BinB200Error(
-                f"{LIB_PATH} not found: build it with `python -m bin_b200.build` (nvcc, sm_100a). "
-                "bin_b200 has no CPU/PyTorch fallback.")
+            # a fresh checkout carries sources only: compile the CUDA library once (12 s with nvcc); if that is not
+            # possible the package is unusable -- there is deliberately no CPU / PyTorch fallback.
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise BinB200Error(
+                    f"{LIB_PATH} not found and building it failed ({e}). Build with `python -m bin_b200.build` "
+                    "(nvcc, sm_100a). bin_b200 has no CPU/PyTorch fallback.") from e
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGS.items():
             fn = getattr(L, name)          # AttributeError here = header/library mismatch

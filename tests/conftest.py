@@ -29,3 +29,10 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """Compile libbin_b200.so if the checkout does not carry it (no-op when the digest stamp matches)."""
+    from bin_b200 import build
+    build.build()
