@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             __syncwarp();
           }
           if (elect_one()) umma_commit(&ctrl->empty[s]);   // frees the smem stage once these MMAs retire
-          __syncwarp();
+          tc_fence_before();                               // order this warp's tcgen05.mma before the flag (the
+          __syncwarp();                                    // other warp pairs it with tc_fence_after above)
           if (lane == 0) ctrl->issued = it + 1;            // hand the tensor pipe to the other MMA warp
           if (Y == 0 && lane == 0) dbg_rec(p, 1, dbg_it, 2);
           ++dbg_it;
