@@ -30,6 +30,11 @@ int launch_pixel_loss_fwd(const float* const* a, const float* const* b, int npai
                           float* pair_loss, cudaStream_t s);
 int launch_pixel_loss_bwd(const float* const* a, const float* const* b, float* const* da, float* const* db, int npairs,
                           size_t n, int kind, float eps, const float* upstream, cudaStream_t s);
+int launch_adam_step(const bin_adam_tensor_t* table, const int* chunk_prefix, int ntensors, int nchunks, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
+                     float bias_correction2, float grad_scale, cudaStream_t s);
+int launch_blur_average_u8(const uint8_t* frames, int T, size_t frame_bytes, int window_size, int first_mid, int stride,
+                           int nwin, uint8_t* out, cudaStream_t s);
 int launch_tensor2img_u8(const float* x, int Hs, int Ws, int top, int left, int h, int w, uint8_t* out, cudaStream_t s);
 int launch_u8_to_frame(const uint8_t* img, int h, int w, int pl, int pr, int pt, int pb, float* out, cudaStream_t s);
 int launch_convlstm_bwd(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
@@ -725,6 +730,19 @@ int bin_pyramid3_fwd(const bin_net_t* net, const float* const* F, float* const* 
   BIN_TRY(run_stage(net, 1, 3, {{{o[0], o[0], o[1]}, o[3]}, {{o[1], o[1], o[2]}, o[4]}}, B, H, W, workspace,
                     workspace_bytes, s));
   return run_stage(net, 2, 5, {{{o[3], F[1], o[3], o[4], F[2]}, o[5]}}, B, H, W, workspace, workspace_bytes, s);
+}
+
+int bin_adam_step(const bin_adam_tensor_t* table_dev, const int* chunk_prefix_dev, int ntensors, int nchunks, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
+                  float bias_correction2, float grad_scale, bin_stream_t s) {
+  if (!table_dev || !chunk_prefix_dev) return fail(BIN_ERR_ARG, "adam_step: null argument");
+  return launch_adam_step(table_dev, chunk_prefix_dev, ntensors, nchunks, lr, beta1, beta2, eps, weight_decay,
+                          bias_correction1, bias_correction2, grad_scale, (cudaStream_t)s);
+}
+int bin_blur_average_u8(const uint8_t* frames, int T, size_t frame_bytes, int window_size, int first_mid, int stride,
+                        int nwin, uint8_t* out, bin_stream_t s) {
+  if (!frames || !out) return fail(BIN_ERR_ARG, "blur_average: null argument");
+  return launch_blur_average_u8(frames, T, frame_bytes, window_size, first_mid, stride, nwin, out, (cudaStream_t)s);
 }
 
 int bin_debug_timeline(long long* host, int n) {

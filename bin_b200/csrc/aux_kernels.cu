@@ -744,6 +744,111 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma2_bench_k
 }
 
 // ------------------------------------------------------------------ launch wrappers
+// ---------------------------------------------------------------------------------------------------------
+// Multi-tensor Adam: torch.optim.Adam.step as bin_model.py:97-100,141 drives it
+// (L2 weight decay folded into the gradient, no amsgrad), one launch over all 540 parameter tensors.
+// Block b owns kAdamChunk consecutive elements of tensor t, t = the last entry with chunk_prefix[t] <= b.
+// HBM-bound: 16 B read + 12 B written per parameter.
+constexpr int kAdamChunk = 4096;
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float lr_bc1, float b1, float b2,
+                                         float eps, float wd, float inv_sqrt_bc2, float gscale) {
+  g = g * gscale;
+  if (wd != 0.f) g = g + wd * p;                       // grad.add(param, alpha=weight_decay)
+  m = m + (g - m) * (1.f - b1);                        // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * b2 + (1.f - b2) * g * g;                     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+  const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;   // (exp_avg_sq.sqrt() / sqrt(bias_correction2)).add_(eps)
+  p = p - lr_bc1 * (m / denom);                        // param.addcdiv_(exp_avg, denom, value=-lr / bias_correction1)
+}
+__global__ void adam_step_kernel(const bin_adam_tensor_t* __restrict__ table, const int* __restrict__ chunk_prefix,
+                                 int ntensors, float lr_bc1, float b1, float b2, float eps, float wd,
+                                 float inv_sqrt_bc2, float gscale) {
+  __shared__ int s_t;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = ntensors - 1;                     // chunk_prefix[0] == 0 <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (chunk_prefix[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    s_t = lo;
+  }
+  __syncthreads();
+  const int t = s_t;
+  const bin_adam_tensor_t T = table[t];
+  const size_t base = (size_t)((int)blockIdx.x - chunk_prefix[t]) * kAdamChunk;
+  const size_t end = (base + kAdamChunk < T.n) ? base + kAdamChunk : (size_t)T.n;
+  float* __restrict__ P = T.p;
+  const float* __restrict__ G = T.g;
+  float* __restrict__ M = T.m;
+  float* __restrict__ V = T.v;
+  const bool vec = ((((uintptr_t)P) | ((uintptr_t)G) | ((uintptr_t)M) | ((uintptr_t)V)) & 15u) == 0;
+  if (vec) {                                           // base is a multiple of 4 elements
+    const size_t end4 = base + ((end - base) & ~(size_t)3);
+    for (size_t i = base + threadIdx.x * 4; i < end4; i += blockDim.x * 4) {
+      float4 p = *reinterpret_cast<float4*>(P + i), m = *reinterpret_cast<float4*>(M + i),
+             v = *reinterpret_cast<float4*>(V + i);
+      const float4 g = *reinterpret_cast<const float4*>(G + i);
+      adam_one(p.x, g.x, m.x, v.x, lr_bc1, b1, b2, eps, wd, inv_sqrt_bc2, gscale);
+      adam_one(p.y, g.y, m.y, v.y, lr_bc1, b1, b2, eps, wd, inv_sqrt_bc2, gscale);
+      adam_one(p.z, g.z, m.z, v.z, lr_bc1, b1, b2, eps, wd, inv_sqrt_bc2, gscale);
+      adam_one(p.w, g.w, m.w, v.w, lr_bc1, b1, b2, eps, wd, inv_sqrt_bc2, gscale);
+      *reinterpret_cast<float4*>(P + i) = p;
+      *reinterpret_cast<float4*>(M + i) = m;
+      *reinterpret_cast<float4*>(V + i) = v;
+    }
+    for (size_t i = end4 + threadIdx.x; i < end; i += blockDim.x) {
+      float p = P[i], m = M[i], v = V[i];
+      adam_one(p, G[i], m, v, lr_bc1, b1, b2, eps, wd, inv_sqrt_bc2, gscale);
+      P[i] = p; M[i] = m; V[i] = v;
+    }
+  } else {
+    for (size_t i = base + threadIdx.x; i < end; i += blockDim.x) {
+      float p = P[i], m = M[i], v = V[i];
+      adam_one(p, G[i], m, v, lr_bc1, b1, b2, eps, wd, inv_sqrt_bc2, gscale);
+      P[i] = p; M[i] = m; V[i] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Blur synthesis: create_dataset_blur_N_frames_average.py:108-134.  Blurry frame w is
+// uint8(sum_j float32(frame[mid_w - r + j]) / float32(n)) with n = 2r+1 sharp frames around mid_w = first_mid + w*stride
+// (float32 sum of <= 256 bytes is exact, one IEEE division, truncation).  One thread = 16 output bytes; the
+// overlapping windows (stride 8 of 11) re-read frames from L2, HBM sees each frame once.
+__global__ void blur_average_u8_kernel(const uint8_t* __restrict__ frames, size_t frame_bytes, int n, int first, int stride,
+                                       int nwin, uint8_t* __restrict__ out, int vec) {
+  const size_t per = vec ? (frame_bytes + 15) / 16 : frame_bytes;
+  const size_t total = per * (size_t)nwin;
+  const float fn = (float)n;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(idx / per);
+    const size_t o = idx - (size_t)w * per;
+    const uint8_t* src = frames + (size_t)(first + w * stride) * frame_bytes;
+    uint8_t* dst = out + (size_t)w * frame_bytes;
+    if (vec && (o + 1) * 16 <= frame_bytes) {
+      unsigned acc[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[k] = 0;
+      for (int j = 0; j < n; ++j) {
+        const uint4 q = *reinterpret_cast<const uint4*>(src + (size_t)j * frame_bytes + o * 16);
+        const unsigned r[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] += (r[k >> 2] >> (8 * (k & 3))) & 0xffu;
+      }
+      unsigned r[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < 16; ++k) r[k >> 2] |= ((unsigned)(__fdiv_rn((float)acc[k], fn)) & 0xffu) << (8 * (k & 3));
+      *reinterpret_cast<uint4*>(dst + o * 16) = make_uint4(r[0], r[1], r[2], r[3]);
+    } else {
+      const size_t b0 = vec ? o * 16 : o, b1 = vec ? frame_bytes : o + 1;
+      for (size_t b = b0; b < b1; ++b) {
+        unsigned acc = 0;
+        for (int j = 0; j < n; ++j) acc += src[(size_t)j * frame_bytes + b];
+        dst[b] = (uint8_t)__fdiv_rn((float)acc, fn);
+      }
+    }
+  }
+}
+
 static inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   const size_t cap = 148 * 16;
@@ -866,6 +971,30 @@ int launch_u8_to_frame(const uint8_t* img, int h, int w, int pl, int pr, int pt,
   if (h < 1 || w < 1 || pl < 0 || pr < 0 || pt < 0 || pb < 0) return fail(BIN_ERR_ARG, "u8_to_frame: bad geometry");
   const int Hp = h + pt + pb, Wp = w + pl + pr;
   u8_to_frame_kernel<<<grid_for((size_t)Hp * Wp, 256), 256, 0, s>>>(img, h, w, pl, pt, Hp, Wp, out);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_adam_step(const bin_adam_tensor_t* table, const int* chunk_prefix, int ntensors, int nchunks, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
+                     float bias_correction2, float grad_scale, cudaStream_t s) {
+  if (ntensors < 1 || nchunks < 1 || !(bias_correction1 > 0.f) || !(bias_correction2 > 0.f))
+    return fail(BIN_ERR_ARG, "adam_step: empty table or non-positive bias correction");
+  adam_step_kernel<<<nchunks, 256, 0, s>>>(table, chunk_prefix, ntensors, lr / bias_correction1, beta1, beta2, eps,
+                                           weight_decay, 1.f / sqrtf(bias_correction2), grad_scale);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_blur_average_u8(const uint8_t* frames, int T, size_t frame_bytes, int window_size, int first_mid, int stride,
+                           int nwin, uint8_t* out, cudaStream_t s) {
+  const int r = (window_size - 1) / 2;                 // average_half_range, script :101
+  const int n = 2 * r + 1;                             // len(mid_list)
+  if (T < 1 || frame_bytes < 1 || window_size < 1 || n > 256 || stride < 0 || nwin < 1 || first_mid - r < 0 ||
+      (long long)first_mid + (long long)(nwin - 1) * stride + r >= T)
+    return fail(BIN_ERR_ARG, "blur_average: window runs outside the T frames (or window_size > 256)");
+  const int vec = ((((uintptr_t)frames) | ((uintptr_t)out) | (uintptr_t)frame_bytes) & 15u) == 0;
+  const size_t per = vec ? frame_bytes / 16 : frame_bytes;
+  blur_average_u8_kernel<<<grid_for(per * (size_t)nwin, 256), 256, 0, s>>>(frames, frame_bytes, n, first_mid - r, stride,
+                                                                          nwin, out, vec);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
 }

@@ -217,6 +217,31 @@ int bin_tensor2img_u8(const float* x, int Hs, int Ws, int top, int left, int h, 
  * fp32 CHW RGB /255 of size (3, h+pad_t+pad_b, w+pad_l+pad_r), edge-replicated. */
 int bin_u8_to_frame(const uint8_t* img, int h, int w, int pad_l, int pad_r, int pad_t, int pad_b, float* out, bin_stream_t s);
 
+/* ---- optimizer step: torch.optim.Adam as bin_model.py:97-100 builds it and :141 steps it ----- */
+/* One launch over every parameter tensor.  table (device): ntensors entries; chunk_prefix (device int[ntensors+1]):
+ * chunk_prefix[t] = number of BIN_ADAM_CHUNK-element blocks before tensor t, chunk_prefix[ntensors] = nchunks.
+ * Semantics of torch.optim.Adam(amsgrad=False, maximize=False): g' = grad_scale*g + weight_decay*p;
+ * m += (g'-m)(1-beta1); v = beta2 v + (1-beta2) g'^2; p -= lr/bias_correction1 * m / (sqrt(v)/sqrt(bias_correction2) + eps)
+ * with bias_correction_i = 1 - beta_i^step computed by the caller (as torch does, on the host). */
+#define BIN_ADAM_CHUNK 4096
+typedef struct {
+  float* p;                 /* parameter (updated in place)        */
+  const float* g;           /* gradient                            */
+  float* m;                 /* exp_avg                             */
+  float* v;                 /* exp_avg_sq                          */
+  unsigned long long n;     /* elements                            */
+} bin_adam_tensor_t;
+int bin_adam_step(const bin_adam_tensor_t* table_dev, const int* chunk_prefix_dev, int ntensors, int nchunks, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
+                  float bias_correction2, float grad_scale, bin_stream_t s);
+
+/* ---- training-data synthesis: create_dataset_blur_N_frames_average.py:108-134 ------------------ */
+/* frames: device uint8 [T][frame_bytes] (consecutive sharp frames, any pixel layout); out: [nwin][frame_bytes].
+ * out[w] = uint8( sum_{j=-r..r} float32(frames[first_mid + w*stride + j]) / float32(2r+1) ), r = (window_size-1)/2
+ * (script: window_size 11, first_mid 16, stride 8, nwin = floor(T/8) - 2). */
+int bin_blur_average_u8(const uint8_t* frames, int T, size_t frame_bytes, int window_size, int first_mid, int stride,
+                        int nwin, uint8_t* out, bin_stream_t s);
+
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* Issue `iters` back-to-back tcgen05.mma (M=128, N=n, K=16, fp16) from one CTA per SM and
  * return cycles per MMA in *cycles_host (host pointer; synchronises). mode 0: A/B K-major

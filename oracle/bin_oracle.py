@@ -285,6 +285,39 @@ def tensor2img_bgr_u8(t: Tensor):
     return (img * 255.0).round().astype(np.uint8)
 
 
+def adam_step(p, g, m, v, step: int, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float):
+    """One torch.optim.Adam step (the optimizer of bin_model.py:97-100,141; torch/optim/adam.py _single_tensor_adam,
+    amsgrad=False) restated on fp32 numpy arrays; returns new (p, m, v).  `step` is the 1-based step number."""
+    import numpy as np
+    f = np.float32
+    if weight_decay != 0:
+        g = g + f(weight_decay) * p
+    m = m + (g - m) * f(1 - beta1)
+    v = v * f(beta2) + f(1 - beta2) * g * g
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    denom = np.sqrt(v) / f(math.sqrt(bc2)) + f(eps)
+    p = p - f(lr / bc1) * (m / denom)
+    return p.astype(f), m.astype(f), v.astype(f)
+
+
+def blur_average(frames_u8, window_size: int = 11, first_mid: int = 16, stride: int = 8, nwin: Optional[int] = None):
+    """create_dataset_blur_N_frames_average.py:99-131 on a (T, ...) uint8 numpy array: blurry frame w is the float32
+    sum of the 2r+1 frames around first_mid + w*stride (r = int((window_size-1)/2), :101), divided by their count
+    (:129) and truncated by .astype("uint8") (:130); nwin defaults to floor(T/8) - 2 (:104)."""
+    import numpy as np
+    T = frames_u8.shape[0]
+    r = int((window_size - 1) / 2)
+    if nwin is None:
+        nwin = math.floor(T / stride) - 2
+    out = []
+    for w in range(nwin):
+        mid = first_mid + w * stride
+        acc = np.zeros(frames_u8.shape[1:], dtype=np.float32)
+        for loc in range(mid - r, mid + r + 1):
+            acc = acc + frames_u8[loc].astype("float32")
+        out.append((acc / np.float32(2 * r + 1)).astype("uint8"))
+    return np.stack(out)
+
 CONV_MACS_PER_PX_WINDOW = 14_234_976          # SURVEY §8d
 def window_flops(H: int, W: int, B: int = 1) -> float:
     return 2.0 * CONV_MACS_PER_PX_WINDOW * H * W * B

@@ -116,3 +116,27 @@ def test_get_loss(golden_dir, kind):
     loss, ll = O.get_loss_6v2(list(g["outs"]), list(g["gts"]), kind)
     assert abs(loss.item() - g[kind].item()) <= 1e-5 * max(1.0, abs(g[kind].item()))
     assert (torch.stack(ll) - g[kind + "_list"]).abs().max().item() <= 1e-4 * max(1.0, g[kind + "_list"].abs().max().item())
+
+
+@pytest.mark.parametrize("tag", ["wd0", "wd"])
+def test_adam(golden_dir, tag):
+    """oracle.adam_step vs three steps of torch.optim.Adam (oracle/make_golden_train.py)."""
+    d = np.load(os.path.join(golden_dir, "adam.npz"))
+    lr, b1, b2, eps, wd = (float(x) for x in d["hyper"])
+    wd = wd if tag == "wd" else 0.0
+    p = d[f"{tag}_p0"].copy()
+    m, v = np.zeros_like(p), np.zeros_like(p)
+    for k in range(3):
+        p, m, v = O.adam_step(p, d[f"{tag}_grads"][k], m, v, k + 1, lr, b1, b2, eps, wd)
+    np.testing.assert_allclose(m, d[f"{tag}_m"], rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(v, d[f"{tag}_v"], rtol=2e-6, atol=1e-12)
+    np.testing.assert_allclose(p, d[f"{tag}_p"], rtol=0, atol=2e-7)      # 3 updates of magnitude lr = 1e-4
+
+
+@pytest.mark.parametrize("ws", [7, 11])
+def test_blur_average(golden_dir, ws):
+    """oracle.blur_average vs the reference script's create_clips_overlap, bit-exact."""
+    d = np.load(os.path.join(golden_dir, "blur_average.npz"))
+    assert list(d[f"ws{ws}_mid"]) == [16, 24, 32, 40]
+    out = O.blur_average(d["frames"], window_size=ws)
+    assert out.dtype == np.uint8 and np.array_equal(out, d[f"ws{ws}_out"])
