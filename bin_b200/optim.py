@@ -46,6 +46,9 @@ class _Table:
         self.prefix = torch.from_numpy(prefix).to(dev)
         self.dev = torch.empty((n, 5), dtype=torch.int64, device=dev)
         self.copied = torch.cuda.Event()
+        self.ids: List[int] = []
+        self.shared_step = None                         # one CPU tensor aliased by every state[p]["step"] of the group
+        self.step_value = 0.0
 
     def upload(self, grads: List[torch.Tensor]) -> None:
         self.copied.synchronize()                       # the previous step's async copy has left the pinned buffer
@@ -63,7 +66,24 @@ class Adam(torch.optim.Optimizer):
         if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1):
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
-        self._tables: Dict[int, _Table] = {}
+        self._tables: Dict[Tuple[int, int], _Table] = {}
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables.clear()                           # exp_avg / exp_avg_sq / step tensors were replaced
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        if hasattr(self, "_tables"):
+            self._tables.clear()
+
+    def _launch(self, tab: _Table, grads: List[torch.Tensor], group, step: float, grad_scale: float) -> None:
+        beta1, beta2 = group["betas"]
+        with torch.cuda.device(tab.dev.device):
+            tab.upload(grads)
+            check(lib().bin_adam_step(tab.dev.data_ptr(), tab.prefix.data_ptr(), tab.n, tab.nchunks,
+                                      float(group["lr"]), beta1, beta2, group["eps"], group["weight_decay"],
+                                      1.0 - beta1 ** step, 1.0 - beta2 ** step, grad_scale, _stream()))
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -72,8 +92,19 @@ class Adam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         for gi, group in enumerate(self.param_groups):
+            params = group["params"]
+            grads = [p.grad for p in params]
+            tab = self._tables.get((gi, 0))
+            # steady state: same parameter objects as last step, every one with a dense contiguous gradient, one shared
+            # step counter -> no per-tensor Python work beyond reading 540 gradient pointers
+            if (tab is not None and tab.shared_step is not None and tab.ids == [id(p) for p in params]
+                    and all(g is not None and g.is_contiguous() for g in grads)):
+                self._launch(tab, grads, group, float(tab.step_value) + 1.0, grad_scale)
+                tab.shared_step += 1
+                tab.step_value += 1
+                continue
             by_step: Dict[float, List[torch.nn.Parameter]] = {}
-            for p in group["params"]:
+            for p in params:
                 if p.grad is None:
                     continue
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
@@ -86,9 +117,7 @@ class Adam(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 by_step.setdefault(float(st["step"]), []).append(p)
-            beta1, beta2 = group["betas"]
             for k, (step0, ps) in enumerate(by_step.items()):
-                step = step0 + 1.0
                 ms = [self.state[p]["exp_avg"] for p in ps]
                 vs = [self.state[p]["exp_avg_sq"] for p in ps]
                 gs = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in ps]
@@ -96,11 +125,16 @@ class Adam(torch.optim.Optimizer):
                 tab = self._tables.get((gi, k))
                 if tab is None or tab.key != key:
                     tab = self._tables[(gi, k)] = _Table(ps, ms, vs)
-                with torch.cuda.device(ps[0].device):
-                    tab.upload(gs)
-                    check(lib().bin_adam_step(tab.dev.data_ptr(), tab.prefix.data_ptr(), tab.n, tab.nchunks,
-                                              float(group["lr"]), beta1, beta2, group["eps"], group["weight_decay"],
-                                              1.0 - beta1 ** step, 1.0 - beta2 ** step, grad_scale, _stream()))
-                for p in ps:
-                    self.state[p]["step"] += 1
+                self._launch(tab, gs, group, step0 + 1.0, grad_scale)
+                tab.ids, tab.shared_step = [id(p) for p in ps], None
+                if len(by_step) == 1 and len(ps) == len(params):
+                    # every tensor of the group is at the same step: let them share ONE counter tensor (state_dict()
+                    # still shows a `step` per parameter; torch.save keeps the aliasing)
+                    tab.shared_step = torch.tensor(step0 + 1.0, dtype=torch.float32)
+                    tab.step_value = step0 + 1.0
+                    for p in ps:
+                        self.state[p]["step"] = tab.shared_step
+                else:
+                    for p in ps:
+                        self.state[p]["step"] = self.state[p]["step"] + 1
         return loss
