@@ -35,6 +35,9 @@ int launch_adam_step(const bin_adam_tensor_t* table, const int* chunk_prefix, in
                      float bias_correction2, float grad_scale, cudaStream_t s);
 int launch_blur_average_u8(const uint8_t* frames, int T, size_t frame_bytes, int window_size, int first_mid, int stride,
                            int nwin, uint8_t* out, cudaStream_t s);
+int launch_rdb_tail(const bin_act_t& x, int x_plane0, const bin_act_t& g, int g_plane0, const void* w_conv,
+                    const float* b_conv, const void* w_lff, const float* b_lff, const bin_act_t& out, int out_plane0,
+                    int b_begin, int b_count, int y_begin, int y_count, cudaStream_t s);
 int launch_tensor2img_u8(const float* x, int Hs, int Ws, int top, int left, int h, int w, uint8_t* out, cudaStream_t s);
 int launch_u8_to_frame(const uint8_t* img, int h, int w, int pl, int pr, int pt, int pb, float* out, cudaStream_t s);
 int launch_convlstm_bwd(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
@@ -200,13 +203,20 @@ static std::vector<Band> plan_bands(int Btot, int h, int w) {
 }
 
 // One RDB: 4 x (conv3x3+ReLU -> growth planes) + LFF 1x1 + residual (RDN.py:149-165).
+// The last conv and the LFF run as one kernel (rdb_tail.cu) in fp16 inference; training keeps them apart because the
+// backward needs the fourth growth map, and the split-fp16 mode has no fused variant.  BIN_B200_FUSE_LFF=0 disables it.
+static bool fuse_lff_enabled() {
+  static const bool on = []() { const char* e = getenv("BIN_B200_FUSE_LFF"); return !(e && *e == '0'); }();
+  return on;
+}
 static int run_rdb(const void* blob, const BackboneLayout& L, int i, const bin_act_t& xin, int x_plane0,
                    const bin_act_t& g, const bin_act_t& out, int out_plane0, const std::vector<Band>& bands,
-                   cudaStream_t s, int g_plane0 = 0, int x3 = 0) {
+                   cudaStream_t s, int g_plane0 = 0, int x3 = 0, bool keep_growth = false) {
   const int base = 2 + i * (kCgrow + 1);
   const int h = xin.H;
+  const bool fuse = !x3 && !keep_growth && fuse_lff_enabled();
   for (const Band& bd : bands) {
-    for (int c = 0; c < kCgrow; ++c) {
+    for (int c = 0; c < (fuse ? kCgrow - 1 : kCgrow); ++c) {
       bin_conv_args_t a = conv_args(blob, L.conv[base + c], x3);
       a.in0 = xin; a.in0_plane0 = x_plane0; a.in0_planes = 12;
       a.in1 = g; a.in1_plane0 = g_plane0; a.in1_planes = 4 * c;
@@ -216,6 +226,15 @@ static int run_rdb(const void* blob, const BackboneLayout& L, int i, const bin_a
       const int lo = bd.y0 - ext < 0 ? 0 : bd.y0 - ext, hi = bd.y1 + ext > h ? h : bd.y1 + ext;
       a.b_begin = bd.b0; a.b_count = bd.nb; a.y_begin = lo; a.y_count = hi - lo;
       BIN_TRY(launch_conv(a, s));
+    }
+    if (fuse) {
+      const ConvSpec& c3 = L.conv[base + kCgrow - 1];
+      const ConvSpec& lf = L.conv[base + kCgrow];
+      BIN_TRY(launch_rdb_tail(xin, x_plane0, g, g_plane0, (const uint8_t*)blob + c3.w_off,
+                              (const float*)((const uint8_t*)blob + c3.b_off), (const uint8_t*)blob + lf.w_off,
+                              (const float*)((const uint8_t*)blob + lf.b_off), out, out_plane0, bd.b0, bd.nb, bd.y0,
+                              bd.y1 - bd.y0, s));
+      continue;
     }
     bin_conv_args_t a = conv_args(blob, L.conv[base + kCgrow], x3);
     a.in0 = xin; a.in0_plane0 = x_plane0; a.in0_planes = 12;
@@ -255,8 +274,8 @@ static int run_backbone(int nframes, const void* blob, const bin_frames_t& fr, i
   const std::vector<Band> bands = plan_bands(Btot, H / 2, W / 2);
   for (int i = 0; i < kD; ++i) {                                                 // RDN.py:215-217
     const int gp0 = train ? 16 * i : 0;
-    if (i == 0) BIN_TRY(run_rdb(blob, L, i, ws.f2, 0, ws.g, ws.cat, 0, bands, s, gp0, x3));
-    else BIN_TRY(run_rdb(blob, L, i, ws.cat, 12 * (i - 1), ws.g, ws.cat, 12 * i, bands, s, gp0, x3));
+    if (i == 0) BIN_TRY(run_rdb(blob, L, i, ws.f2, 0, ws.g, ws.cat, 0, bands, s, gp0, x3, train));
+    else BIN_TRY(run_rdb(blob, L, i, ws.cat, 12 * (i - 1), ws.g, ws.cat, 12 * i, bands, s, gp0, x3, train));
   }
   {
     bin_conv_args_t a = conv_args(blob, L.conv[62], x3);                             // GFF.0 on the 1152-ch concat (RDN.py:218)

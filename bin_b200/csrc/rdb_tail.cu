@@ -1,0 +1,386 @@
+// bin_b200 -- fused tail of a residual dense block for sm_100a:
+//   g3 = ReLU(conv3x3(cat(x, g0, g1, g2)))        RDN.py:141-147 (RDB_Conv, the 4th of RDN.py:156-160)
+//   x' = LFF(cat(x, g0, g1, g2, g3)) + x          RDN.py:162-165 (1x1 conv 224 -> 96, local residual)
+// in ONE kernel.  Layer by layer these two move 448 + 832 bytes per position through HBM and are bound by it
+// (DESIGN.md 5); fused, the 192 input channels are fetched once (the 1x1 LFF reads the centre of the very halo tile
+// the 3x3 conv already has in shared memory), g3 never leaves the SM, and only x' is written: 768 bytes per position.
+//
+// GEMM view per 128-pixel tile (4 rows x 32-pixel smem pitch, 30 valid columns) and 32-channel chunk c = 0..5:
+//   conv accumulator  (128 x 96, the three kx taps stacked in N as in conv_igemm.cu)  += A(ky) * Wc[c][ky],  ky = 0..2
+//   LFF accumulator   (128 x 96)                                                      += A(centre) * Wl[c]
+// then, once the conv accumulator is complete, the epilogue-A warps add the kx column groups (warp shuffles), apply
+// bias + ReLU, and write g3 of the tile as a K-major fp16 operand into shared memory, and ONE more K = 32 step
+//   LFF accumulator += g3 * Wl[6]
+// finishes x'.  That "tail" step of tile t is issued AFTER the main loop of tile t+1, so the tensor pipe never waits
+// for the epilogue: TMEM holds two conv accumulators and three LFF accumulators (2*96 + 3*96 = 480 columns).
+// All weights (6 x 4 slabs + 1 = 150 KB) stay resident in shared memory; activations stream through a 4-stage ring.
+//
+// Warp roles (384 threads, 1 CTA/SM, persistent):
+//   warp 0 lane 0 : TMA producer              warp 2 : TMEM allocator
+//   warps 1, 3    : cooperating tcgen05.mma issuers (same hand-off scheme as conv_igemm.cu)
+//   warps 4..7    : epilogue A (conv accumulator -> g3 tile in smem), one TMEM lane quarter each
+//   warps 8..11   : epilogue B (LFF accumulator + bias + residual -> P8 store)
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace binb {
+
+constexpr int kRtTH = 4;                               // output rows per tile (one 128-row accumulator)
+constexpr int kRtRows = kRtTH + 2;                     // + 3x3 halo
+constexpr int kRtTW = kTWH - 2;                        // valid output columns per tile
+constexpr int kRtAPlane = kRtRows * kTWH * 16;         // bytes of one 8-channel plane of a stage
+constexpr int kRtABytes = kKPL * kRtAPlane;            // 12 288
+constexpr int kRtN = 96;                               // N of every MMA (3 kx x 32 conv channels, or the 96 LFF channels)
+constexpr int kRtSlab = kKPL * kRtN * 16;              // [4 planes][96 rows][16 B] = 6 144
+constexpr int kRtChunks = 6;                           // 192 input channels of the conv
+constexpr int kRtWChunk = 4 * kRtSlab;                 // conv ky = 0,1,2 + LFF slab of the chunk
+constexpr int kRtWBytes = kRtChunks * kRtWChunk + kRtSlab;   // + the LFF slab of the g3 channels
+constexpr int kRtHPlane = 128 * 16;
+constexpr int kRtHBytes = kKPL * kRtHPlane;            // g3 tile: [4 planes][128 pixels][16 B]
+constexpr int kRtStages = 4;
+constexpr int kRtSmem = kCtrlBytes + kRtWBytes + 2 * kRtHBytes + kRtStages * kRtABytes;
+constexpr int kRtLffCol0 = 2 * kRtN;                   // TMEM: conv[a] at a*96, lff[l] at 192 + l*96
+static_assert(kRtSmem <= kSmemMax, "rdb_tail shared memory");
+static_assert(kRtWBytes % 1024 == 0 && kRtHBytes % 1024 == 0, "operand alignment");
+
+struct alignas(64) RdbTailParams {
+  CUtensorMap tmap0, tmap1;             // x planes, growth planes
+  int plane0_0, plane0_1;
+  const uint8_t* w_conv;                // conv_igemm SX pack: [chunk][ky][4][kx*32+co][8]
+  const uint8_t* w_lff;                 // conv_igemm 1x1 pack: [chunk][4][co][8]
+  const float* b_conv;
+  const float* b_lff;
+  int H, W;
+  int b0, y0, ny;
+  int tiles_x, tiles_y, ntiles;
+  __half* out; int out_planes, out_plane0;
+  const __half* res; int res_planes, res_plane0;
+};
+
+struct RtCtrl {
+  uint64_t full[kRtStages], empty[kRtStages];
+  uint64_t wfull[kRtChunks + 1];
+  uint64_t conv_full[2], conv_empty[2];
+  uint64_t lff_full[3], lff_empty[3];
+  uint64_t h_full[2], h_empty[2];
+  uint32_t tmem_base;
+  volatile uint32_t issued;
+};
+static_assert(sizeof(RtCtrl) <= 512, "ctrl block");
+
+__device__ __forceinline__ uint32_t rt_pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 rt_unpack_h2(uint32_t u) {
+  __half2 h = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(h);
+}
+
+__global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant__ RdbTailParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  RtCtrl* ctrl = reinterpret_cast<RtCtrl*>(smem);
+  float* sb_conv = reinterpret_cast<float*>(smem + 1024);          // 32 floats
+  float* sb_lff = sb_conv + 32;                                    // 96 floats
+  uint8_t* res_w = smem + kCtrlBytes;
+  uint8_t* htile = res_w + kRtWBytes;
+  uint8_t* stage0 = htile + 2 * kRtHBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmap0);
+    tma_prefetch_desc(&p.tmap1);
+    for (int i = 0; i < kRtStages; ++i) { mbar_init(&ctrl->full[i], 1); mbar_init(&ctrl->empty[i], 1); }
+    for (int i = 0; i <= kRtChunks; ++i) mbar_init(&ctrl->wfull[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctrl->conv_full[i], 2);       // one tcgen05.commit per MMA warp
+      mbar_init(&ctrl->conv_empty[i], 128);    // the four epilogue-A warps
+      mbar_init(&ctrl->h_full[i], 128);
+      mbar_init(&ctrl->h_empty[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&ctrl->lff_full[i], 1);
+      mbar_init(&ctrl->lff_empty[i], 128);     // the four epilogue-B warps
+    }
+    ctrl->issued = 0;
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) sb_conv[threadIdx.x] = p.b_conv[threadIdx.x];
+  else if (threadIdx.x < 128) sb_lff[threadIdx.x - 32] = p.b_lff[threadIdx.x - 32];
+  if (warp == 2) {
+    tmem_alloc(&ctrl->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    // ========================================================== TMA producer
+    for (int c = 0; c < kRtChunks; ++c) {
+      mbar_expect_tx(&ctrl->wfull[c], kRtWChunk);
+      bulk_load_1d(res_w + c * kRtWChunk, p.w_conv + (size_t)c * 3 * kRtSlab, 3 * kRtSlab, &ctrl->wfull[c]);
+      bulk_load_1d(res_w + c * kRtWChunk + 3 * kRtSlab, p.w_lff + (size_t)c * kRtSlab, kRtSlab, &ctrl->wfull[c]);
+    }
+    mbar_expect_tx(&ctrl->wfull[kRtChunks], kRtSlab);
+    bulk_load_1d(res_w + kRtChunks * kRtWChunk, p.w_lff + (size_t)kRtChunks * kRtSlab, kRtSlab, &ctrl->wfull[kRtChunks]);
+    uint32_t s = 0, ph = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      int t = tile;
+      const int txi = t % p.tiles_x; t /= p.tiles_x;
+      const int tyi = t % p.tiles_y;
+      const int b = p.b0 + t / p.tiles_y;
+      const int x0 = txi * kRtTW - 1, y0 = p.y0 + tyi * kRtTH - 1;
+      for (int c = 0; c < kRtChunks; ++c) {
+        mbar_wait(&ctrl->empty[s], ph ^ 1);
+        mbar_expect_tx(&ctrl->full[s], kRtABytes);
+        const bool seg1 = c >= 3;
+        tma_load_4d(stage0 + (size_t)s * kRtABytes, seg1 ? (const void*)&p.tmap1 : (const void*)&p.tmap0, &ctrl->full[s],
+                    x0 * 8, y0, seg1 ? p.plane0_1 + (c - 3) * kKPL : p.plane0_0 + c * kKPL, b);
+        if (++s == kRtStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ========================================================== MMA issuers (warp converged, one elected lane)
+    const uint32_t Y = warp >> 1;
+    constexpr uint32_t idesc = umma_idesc_f16(128, kRtN);
+    constexpr uint32_t D_HI = (128u >> 4) | (1u << 14);                // SBO = 128 B, descriptor version 1
+    constexpr uint32_t A_LBO = ((uint32_t)kRtAPlane >> 4) << 16;
+    constexpr uint32_t B_LBO = ((uint32_t)(kRtN * 16) >> 4) << 16;
+    constexpr uint32_t H_LBO = ((uint32_t)kRtHPlane >> 4) << 16;
+    uint32_t it = 0, s = 0, ph = 0, tl = 0;
+    auto wait_turn = [&](uint32_t item) {       // items are issued strictly in order, alternating between the two warps
+      uint32_t spins = 0;
+      while (ctrl->issued < item) {
+        __nanosleep(32);
+        if (++spins > (1u << 24)) {
+          if (lane == 0) printf("bin_b200: rdb_tail hand-off watchdog (block %d item %u)\n", blockIdx.x, item);
+          __trap();
+        }
+      }
+      tc_fence_after();
+    };
+    auto pass_turn = [&](uint32_t item) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ctrl->issued = item + 1;
+    };
+    // tail of local tile pt: LFF accumulator += g3 tile * Wl[6]
+    auto tail_item = [&](uint32_t pt) {
+      const uint32_t hb = pt & 1, plb = pt % 3;
+      mbar_wait(&ctrl->h_full[hb], (pt >> 1) & 1);                     // both warps observe every phase
+      if ((it & 1u) == Y) {
+        if (pt == 0) mbar_wait(&ctrl->wfull[kRtChunks], 0);
+        wait_turn(it);
+        const uint32_t a_lo = ((smem_u32(htile + hb * kRtHBytes) >> 4) & 0x3FFFu) | H_LBO;
+        const uint32_t b_lo = ((smem_u32(res_w + kRtChunks * kRtWChunk) >> 4) & 0x3FFFu) | B_LBO;
+        const uint32_t d = tmem_base + kRtLffCol0 + plb * kRtN;
+        if (elect_one()) {
+#pragma unroll
+          for (int jj = 0; jj < kKC / 16; ++jj) {
+            const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + jj * 2 * (kRtHPlane >> 4));
+            const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + jj * 2 * kRtN);
+            umma_f16_ss(d, ad, bd, idesc, 1u);
+          }
+          umma_commit(&ctrl->lff_full[plb]);
+          umma_commit(&ctrl->h_empty[hb]);
+        }
+        __syncwarp();
+        pass_turn(it);
+      }
+      ++it;
+    };
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tl) {
+      const uint32_t as = tl & 1, lb = tl % 3;
+      mbar_wait(&ctrl->conv_empty[as], ((tl >> 1) & 1) ^ 1);
+      mbar_wait(&ctrl->lff_empty[lb], ((tl / 3) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_conv = tmem_base + as * kRtN;
+      const uint32_t d_lff = tmem_base + kRtLffCol0 + lb * kRtN;
+      for (int c = 0; c < kRtChunks; ++c, ++it) {
+        mbar_wait(&ctrl->full[s], ph);                                 // both warps observe every phase
+        if ((it & 1u) == Y) {
+          if (tl == 0) mbar_wait(&ctrl->wfull[c], 0);
+          wait_turn(it);
+          const uint32_t a_lo = ((smem_u32(stage0 + (size_t)s * kRtABytes) >> 4) & 0x3FFFu) | A_LBO;
+          const uint32_t b_lo = ((smem_u32(res_w + c * kRtWChunk) >> 4) & 0x3FFFu) | B_LBO;
+          const uint32_t first = (c == 0) ? 0u : 1u;
+          if (elect_one()) {
+#pragma unroll
+            for (int jj = 0; jj < kKC / 16; ++jj) {
+              const uint32_t a_k = a_lo + jj * 2 * (kRtAPlane >> 4);
+              const uint32_t b_k = b_lo + jj * 2 * kRtN;
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {                         // conv: A shifted by ky rows, B = slab ky
+                const uint64_t ad = ((uint64_t)D_HI << 32) | (a_k + ky * kTWH);
+                const uint64_t bd = ((uint64_t)D_HI << 32) | (b_k + ky * (kRtSlab >> 4));
+                umma_f16_ss(d_conv, ad, bd, idesc, (jj == 0 && ky == 0) ? first : 1u);
+              }
+              {                                                        // LFF: centre tap (ky = 1, kx = 1), B = slab 3
+                const uint64_t ad = ((uint64_t)D_HI << 32) | (a_k + kTWH + 1);
+                const uint64_t bd = ((uint64_t)D_HI << 32) | (b_k + 3 * (kRtSlab >> 4));
+                umma_f16_ss(d_lff, ad, bd, idesc, jj == 0 ? first : 1u);
+              }
+            }
+            umma_commit(&ctrl->empty[s]);                              // frees the smem stage once these MMAs retire
+          }
+          __syncwarp();
+          pass_turn(it);
+        }
+        if (++s == kRtStages) { s = 0; ph ^= 1; }
+      }
+      if (elect_one()) umma_commit(&ctrl->conv_full[as]);              // this warp's share of the tile's conv MMAs
+      __syncwarp();
+      if (tl > 0) tail_item(tl - 1);
+    }
+    if (tl > 0) tail_item(tl - 1);
+  } else if (warp >= 4 && warp < 8) {
+    // ========================================================== epilogue A: conv accumulator -> g3 tile (smem)
+    const int q = warp & 3;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tl) {
+      const uint32_t as = tl & 1, uph = (tl >> 1) & 1;
+      mbar_wait(&ctrl->conv_full[as], uph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kRtN;
+      uint32_t v[96];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) tmem_ld16(taddr + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&ctrl->conv_empty[as]);                              // accumulator is in registers: release it now
+      // out[p] = D[p][kx=0] + D[p+1][kx=1] + D[p+2][kx=2]  (p+1, p+2 are lanes +1, +2: one warp = one tile row)
+      uint4 o[4];
+      uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float f[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[32 + i + e]), 1);
+          const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[64 + i + e]), 2);
+          f[e] = fmaxf(((__uint_as_float(v[i + e]) + b1) + b2) + sb_conv[i + e], 0.f);
+        }
+        ow[i >> 1] = rt_pack_h2(f[0], f[1]);
+      }
+      mbar_wait(&ctrl->h_empty[as], uph ^ 1);                          // tail of tile tl-2 has consumed this buffer
+      uint8_t* h = htile + as * kRtHBytes + (q * 32 + lane) * 16;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(h + k * kRtHPlane) = o[k];
+      fence_proxy_async();                                             // generic-proxy stores -> visible to tcgen05.mma
+      mbar_arrive(&ctrl->h_full[as]);
+    }
+  } else if (warp >= 8) {
+    // ========================================================== epilogue B: LFF accumulator + bias + x -> x'
+    const int q = warp & 3;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tl) {
+      int t = tile;
+      const int txi = t % p.tiles_x; t /= p.tiles_x;
+      const int tyi = t % p.tiles_y;
+      const int b = p.b0 + t / p.tiles_y;
+      const int y = p.y0 + tyi * kRtTH + q, x = txi * kRtTW + lane;
+      const bool valid = (lane < kRtTW) && (y < p.y0 + p.ny) && (x < p.W);
+      const uint32_t lb = tl % 3;
+      uint4 rbuf[12];                                                  // residual x (RDN.py:165), fetched before the wait
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const size_t off = ((((size_t)b * p.res_planes + p.res_plane0 + k) * p.H + y) * p.W + x) * 8;
+        rbuf[k] = valid ? *reinterpret_cast<const uint4*>(p.res + off) : make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait(&ctrl->lff_full[lb], (tl / 3) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kRtLffCol0 + lb * kRtN;
+#pragma unroll
+      for (int g0 = 0; g0 < kRtN; g0 += 48) {
+        uint32_t v[48];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) tmem_ld16(taddr + g0 + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
+        tmem_ld_wait();
+        if (g0 == 48) {                                                // all 96 columns are in registers
+          tc_fence_before();
+          mbar_arrive(&ctrl->lff_empty[lb]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const uint4 r = rbuf[g0 / 8 + k];
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 g = rt_unpack_h2(rr[i]);
+              const int n = g0 + 8 * k + 2 * i;
+              ow[i] = rt_pack_h2((__uint_as_float(v[8 * k + 2 * i]) + sb_lff[n]) + g.x,
+                                 (__uint_as_float(v[8 * k + 2 * i + 1]) + sb_lff[n + 1]) + g.y);
+            }
+            const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + g0 / 8 + k) * p.H + y) * p.W + x) * 8;
+            *reinterpret_cast<uint4*>(p.out + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+        }
+      }
+    }
+  }
+
+  // ------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+int make_p8_tmap(CUtensorMap* m, const bin_act_t& t, int box_rows);   // conv_igemm.cu
+
+int launch_rdb_tail(const bin_act_t& x, int x_plane0, const bin_act_t& g, int g_plane0, const void* w_conv,
+                    const float* b_conv, const void* w_lff, const float* b_lff, const bin_act_t& out, int out_plane0,
+                    int b_begin, int b_count, int y_begin, int y_count, cudaStream_t s) {
+  const int H = x.H, W = x.W, B = x.B;
+  if (g.H != H || g.W != W || g.B != B || out.H != H || out.W != W || out.B != B)
+    return fail(BIN_ERR_ARG, "rdb_tail: tensor geometry mismatch");
+  if (x_plane0 + 12 > x.planes || g_plane0 + 12 > g.planes || out_plane0 + 12 > out.planes)
+    return fail(BIN_ERR_ARG, "rdb_tail: plane range exceeds tensor");
+  RdbTailParams p;
+  memset(&p, 0, sizeof(p));
+  BIN_TRY(make_p8_tmap(&p.tmap0, x, kRtRows));
+  BIN_TRY(make_p8_tmap(&p.tmap1, g, kRtRows));
+  p.plane0_0 = x_plane0; p.plane0_1 = g_plane0;
+  p.w_conv = reinterpret_cast<const uint8_t*>(w_conv); p.w_lff = reinterpret_cast<const uint8_t*>(w_lff);
+  p.b_conv = b_conv; p.b_lff = b_lff;
+  p.H = H; p.W = W;
+  p.b0 = b_begin; p.y0 = y_begin;
+  const int nb = b_count > 0 ? b_count : B - b_begin;
+  p.ny = y_count > 0 ? y_count : H - y_begin;
+  if (p.b0 < 0 || p.y0 < 0 || nb < 1 || p.ny < 1 || p.b0 + nb > B || p.y0 + p.ny > H)
+    return fail(BIN_ERR_ARG, "rdb_tail: batch/row sub-range outside the tensor");
+  p.tiles_x = (W + kRtTW - 1) / kRtTW;
+  p.tiles_y = (p.ny + kRtTH - 1) / kRtTH;
+  p.ntiles = nb * p.tiles_x * p.tiles_y;
+  p.out = reinterpret_cast<__half*>(out.ptr); p.out_planes = out.planes; p.out_plane0 = out_plane0;
+  p.res = reinterpret_cast<const __half*>(x.ptr); p.res_planes = x.planes; p.res_plane0 = x_plane0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    BIN_CUDA_OK(cudaFuncSetAttribute(rdb_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem));
+    attr_done = true;
+  }
+  static int sms = []() {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  const int grid = p.ntiles < sms ? p.ntiles : sms;
+  rdb_tail_kernel<<<grid, 384, kRtSmem, s>>>(p);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+
+}  // namespace binb

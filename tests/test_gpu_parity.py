@@ -65,6 +65,23 @@ def test_rdb_golden(golden_dir, net):
     assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("B,H,W", [(1, 4, 30), (2, 6, 34), (1, 10, 64), (3, 5, 31), (1, 2, 2), (2, 48, 100), (1, 129, 61)])
+def test_rdb_shapes_vs_oracle(net, sd, B, H, W):
+    """The fused conv3 + LFF tail (rdb_tail.cu: 4-row x 30-column tiles, pipelined over tiles) on ragged sizes:
+    partial tiles in x and y, single-tile launches, several tiles per CTA (129 x 61 = 99 tiles... x B)."""
+    from bin_b200._lib import check, lib
+    prefix = "model.model3_1.RDBs.7"
+    x = torch.randn((B, 96, H, W), generator=torch.Generator().manual_seed(H * 131 + W))
+    ref = O.rdb(x, sd, prefix)
+    blob = net.model.model3_1.packed_blob()                 # bin_rdb_fwd = the backbone's own RDB walker (run_rdb)
+    xc, y = x.cuda(), torch.empty((B, 96, H, W), device="cuda")
+    ws = torch.empty(B * 40 * H * W * 16 + 1024, dtype=torch.uint8, device="cuda")
+    check(lib().bin_rdb_fwd(blob.data_ptr(), 5, 7, xc.data_ptr(), y.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(),
+                            torch.cuda.current_stream().cuda_stream))
+    y = y.cpu()
+    assert torch.isfinite(y).all()
+    assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+
 @pytest.mark.parametrize("name,n", [("model1_1", 2), ("model2_1", 3), ("model3_1", 5), ("model4_1", 5)])
 def test_backbone_golden(golden_dir, net, name, n):
     g = _load(golden_dir, f"backbone_{name}.npz")
