@@ -205,9 +205,9 @@ static std::vector<Band> plan_bands(int Btot, int h, int w) {
 // One RDB: 4 x (conv3x3+ReLU -> growth planes) + LFF 1x1 + residual (RDN.py:149-165).
 // The last conv and the LFF run as one kernel (rdb_tail.cu) in fp16 inference; training keeps them apart because the
 // backward needs the fourth growth map, and the split-fp16 mode has no fused variant.  BIN_B200_FUSE_LFF=0 disables it.
-static bool fuse_lff_enabled() {
-  static const bool on = []() { const char* e = getenv("BIN_B200_FUSE_LFF"); return !(e && *e == '0'); }();
-  return on;
+static bool fuse_lff_enabled() {     // read per call (48 per window) so that tools can A/B it inside one process
+  const char* e = getenv("BIN_B200_FUSE_LFF");
+  return !(e && *e == '0');
 }
 static int run_rdb(const void* blob, const BackboneLayout& L, int i, const bin_act_t& xin, int x_plane0,
                    const bin_act_t& g, const bin_act_t& out, int out_plane0, const std::vector<Band>& bands,

@@ -17,7 +17,8 @@
 //
 // Warp roles (384 threads, 1 CTA/SM, persistent):
 //   warp 0 lane 0 : TMA producer              warp 2 : TMEM allocator
-//   warps 1, 3    : cooperating tcgen05.mma issuers (same hand-off scheme as conv_igemm.cu)
+//   warps 1, 3    : cooperating tcgen05.mma issuers: alternate 8-MMA stage items, one warp's barrier polls overlap
+//                   the other's issue phase
 //   warps 4..7    : epilogue A (conv accumulator -> g3 tile in smem), one TMEM lane quarter each
 //   warps 8..11   : epilogue B (LFF accumulator + bias + residual -> P8 store)
 #include <stdio.h>
@@ -40,10 +41,13 @@ constexpr int kRtWChunk = 4 * kRtSlab;                 // conv ky = 0,1,2 + LFF 
 constexpr int kRtWBytes = kRtChunks * kRtWChunk + kRtSlab;   // + the LFF slab of the g3 channels
 constexpr int kRtHPlane = 128 * 16;
 constexpr int kRtHBytes = kKPL * kRtHPlane;            // g3 tile: [4 planes][128 pixels][16 B]
-constexpr int kRtStages = 4;
-constexpr int kRtSmem = kCtrlBytes + kRtWBytes + 2 * kRtHBytes + kRtStages * kRtABytes;
+constexpr int kRtStages = 4;                            // even: each MMA warp owns two fixed slots (5 slots were not faster)
+constexpr int kRtCtrl = 1024;                          // barriers + counters (512 B) and the two bias vectors (512 B)
+constexpr int kRtSmem = kRtCtrl + kRtWBytes + 2 * kRtHBytes + kRtStages * kRtABytes;
 constexpr int kRtLffCol0 = 2 * kRtN;                   // TMEM: conv[a] at a*96, lff[l] at 192 + l*96
 static_assert(kRtSmem <= kSmemMax, "rdb_tail shared memory");
+static_assert(kRtStages % 2 == 0 && kRtChunks % 2 == 0, "slot ownership by parity");
+
 static_assert(kRtWBytes % 1024 == 0 && kRtHBytes % 1024 == 0, "operand alignment");
 
 struct alignas(64) RdbTailParams {
@@ -58,7 +62,13 @@ struct alignas(64) RdbTailParams {
   int tiles_x, tiles_y, ntiles;
   __half* out; int out_planes, out_plane0;
   const __half* res; int res_planes, res_plane0;
+  int debug; long long* dbg;            // BIN_B200_DEBUG=8: block 0 records clock64 at role milestones (tools only)
 };
+// timeline layout (bin_debug_timeline): [role][iter][4]; role 0 = producer (k 0,1 per stage) and epilogue B (k 2,3 per tile),
+// role 1 = MMA warp 1 (per item it owns: before / after the data wait, after the turn wait, after the issue), role 2 = epilogue A
+__device__ __forceinline__ void rt_rec(const RdbTailParams& p, int role, uint32_t iter, int k) {
+  if ((p.debug & 8) && blockIdx.x == 0 && iter < 1024) p.dbg[role * 4096 + iter * 4 + k] = clock64();
+}
 
 struct RtCtrl {
   uint64_t full[kRtStages], empty[kRtStages];
@@ -67,7 +77,7 @@ struct RtCtrl {
   uint64_t lff_full[3], lff_empty[3];
   uint64_t h_full[2], h_empty[2];
   uint32_t tmem_base;
-  volatile uint32_t issued;
+  volatile uint32_t issued;       // stage items issued so far (hand-off between the two MMA warps)
 };
 static_assert(sizeof(RtCtrl) <= 512, "ctrl block");
 
@@ -80,12 +90,17 @@ __device__ __forceinline__ float2 rt_unpack_h2(uint32_t u) {
   return __half22float2(h);
 }
 
+// ALIGNED: the LFF's centre tap reads the A tile at the x-unshifted start (row offset 32, 512-byte aligned) like the
+// x-stacked conv taps, so its accumulator row p holds output pixel p-1: the g3 tile is stored one row down and epilogue B
+// takes its values from lane+1.  !ALIGNED shifts the descriptor start by one 16-byte row instead (no shuffles, but
+// every 8-row core matrix of that operand then straddles two 128-byte shared-memory lines).
+template <bool ALIGNED>
 __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant__ RdbTailParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   RtCtrl* ctrl = reinterpret_cast<RtCtrl*>(smem);
-  float* sb_conv = reinterpret_cast<float*>(smem + 1024);          // 32 floats
+  float* sb_conv = reinterpret_cast<float*>(smem + 512);           // 32 floats
   float* sb_lff = sb_conv + 32;                                    // 96 floats
-  uint8_t* res_w = smem + kCtrlBytes;
+  uint8_t* res_w = smem + kRtCtrl;
   uint8_t* htile = res_w + kRtWBytes;
   uint8_t* stage0 = htile + 2 * kRtHBytes;
 
@@ -130,15 +145,17 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
     }
     mbar_expect_tx(&ctrl->wfull[kRtChunks], kRtSlab);
     bulk_load_1d(res_w + kRtChunks * kRtWChunk, p.w_lff + (size_t)kRtChunks * kRtSlab, kRtSlab, &ctrl->wfull[kRtChunks]);
-    uint32_t s = 0, ph = 0;
+    uint32_t s = 0, ph = 0, pit = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int t = tile;
       const int txi = t % p.tiles_x; t /= p.tiles_x;
       const int tyi = t % p.tiles_y;
       const int b = p.b0 + t / p.tiles_y;
       const int x0 = txi * kRtTW - 1, y0 = p.y0 + tyi * kRtTH - 1;
-      for (int c = 0; c < kRtChunks; ++c) {
+      for (int c = 0; c < kRtChunks; ++c, ++pit) {
+        rt_rec(p, 0, pit, 0);
         mbar_wait(&ctrl->empty[s], ph ^ 1);
+        rt_rec(p, 0, pit, 1);
         mbar_expect_tx(&ctrl->full[s], kRtABytes);
         const bool seg1 = c >= 3;
         tma_load_4d(stage0 + (size_t)s * kRtABytes, seg1 ? (const void*)&p.tmap1 : (const void*)&p.tmap0, &ctrl->full[s],
@@ -148,18 +165,26 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
     }
   } else if (warp == 1 || warp == 3) {
     // ========================================================== MMA issuers (warp converged, one elected lane)
+    // Measured on B200: an mbarrier poll costs 200-350 cycles even when the phase is complete and the tcgen05 queue is
+    // shallow, so a warp that polls between its 8-MMA items idles the tensor pipe.  Two warps alternate items: stage
+    // item c of a tile belongs to warp c & 1 (6 items per tile, 4 ring slots: a warp always meets the same two slots
+    // and waits only on those), so one warp's barrier poll and descriptor setup overlap the other's issue phase; a
+    // shared-memory counter hands the pipe over in strict item order (deterministic accumulation order).  The
+    // accumulators are zeroed by item 0, so warp A alone waits for them to be free.  The tail of the previous tile
+    // targets an accumulator nobody else touches: warp B issues it after its last item, outside the ordered sequence.
+    // (Tried and slower, see DESIGN.md: one issuing warp fed by a "scout" warp that does all the polling; 16-MMA items;
+    // a 5-slot ring.)
     const uint32_t Y = warp >> 1;
     constexpr uint32_t idesc = umma_idesc_f16(128, kRtN);
     constexpr uint32_t D_HI = (128u >> 4) | (1u << 14);                // SBO = 128 B, descriptor version 1
     constexpr uint32_t A_LBO = ((uint32_t)kRtAPlane >> 4) << 16;
     constexpr uint32_t B_LBO = ((uint32_t)(kRtN * 16) >> 4) << 16;
     constexpr uint32_t H_LBO = ((uint32_t)kRtHPlane >> 4) << 16;
-    uint32_t it = 0, s = 0, ph = 0, tl = 0;
-    auto wait_turn = [&](uint32_t item) {       // items are issued strictly in order, alternating between the two warps
+    uint32_t sit = 0, s = 0, ph = 0, tl = 0, dit = 0;
+    auto wait_turn = [&](uint32_t item) {
       uint32_t spins = 0;
       while (ctrl->issued < item) {
-        __nanosleep(32);
-        if (++spins > (1u << 24)) {
+        if (++spins > (1u << 26)) {
           if (lane == 0) printf("bin_b200: rdb_tail hand-off watchdog (block %d item %u)\n", blockIdx.x, item);
           __trap();
         }
@@ -171,82 +196,91 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
       __syncwarp();
       if (lane == 0) ctrl->issued = item + 1;
     };
-    // tail of local tile pt: LFF accumulator += g3 tile * Wl[6]
+    // tail of local tile pt (warp B): LFF accumulator += g3 tile * Wl[6]
     auto tail_item = [&](uint32_t pt) {
       const uint32_t hb = pt & 1, plb = pt % 3;
-      mbar_wait(&ctrl->h_full[hb], (pt >> 1) & 1);                     // both warps observe every phase
-      if ((it & 1u) == Y) {
-        if (pt == 0) mbar_wait(&ctrl->wfull[kRtChunks], 0);
-        wait_turn(it);
-        const uint32_t a_lo = ((smem_u32(htile + hb * kRtHBytes) >> 4) & 0x3FFFu) | H_LBO;
-        const uint32_t b_lo = ((smem_u32(res_w + kRtChunks * kRtWChunk) >> 4) & 0x3FFFu) | B_LBO;
-        const uint32_t d = tmem_base + kRtLffCol0 + plb * kRtN;
-        if (elect_one()) {
+      const uint32_t a_lo = ((smem_u32(htile + hb * kRtHBytes) >> 4) & 0x3FFFu) | H_LBO;
+      const uint32_t b_lo = ((smem_u32(res_w + kRtChunks * kRtWChunk) >> 4) & 0x3FFFu) | B_LBO;
+      const uint32_t d = tmem_base + kRtLffCol0 + plb * kRtN;
+      mbar_wait(&ctrl->h_full[hb], (pt >> 1) & 1);
+      if (pt == 0) mbar_wait(&ctrl->wfull[kRtChunks], 0);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-          for (int jj = 0; jj < kKC / 16; ++jj) {
-            const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + jj * 2 * (kRtHPlane >> 4));
-            const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + jj * 2 * kRtN);
-            umma_f16_ss(d, ad, bd, idesc, 1u);
-          }
-          umma_commit(&ctrl->lff_full[plb]);
-          umma_commit(&ctrl->h_empty[hb]);
+        for (int jj = 0; jj < kKC / 16; ++jj) {
+          const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + jj * 2 * (kRtHPlane >> 4));
+          const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + jj * 2 * kRtN);
+          umma_f16_ss(d, ad, bd, idesc, 1u);
         }
-        __syncwarp();
-        pass_turn(it);
+        umma_commit(&ctrl->lff_full[plb]);
+        umma_commit(&ctrl->h_empty[hb]);
       }
-      ++it;
+      __syncwarp();
     };
+    const uint32_t stage_lo = ((smem_u32(stage0) >> 4) & 0x3FFFu) | A_LBO;
+    const uint32_t w_lo = ((smem_u32(res_w) >> 4) & 0x3FFFu) | B_LBO;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tl) {
       const uint32_t as = tl & 1, lb = tl % 3;
-      mbar_wait(&ctrl->conv_empty[as], ((tl >> 1) & 1) ^ 1);
-      mbar_wait(&ctrl->lff_empty[lb], ((tl / 3) & 1) ^ 1);
-      tc_fence_after();
+      if (Y == 0) {
+        mbar_wait(&ctrl->conv_empty[as], ((tl >> 1) & 1) ^ 1);
+        mbar_wait(&ctrl->lff_empty[lb], ((tl / 3) & 1) ^ 1);
+      }
       const uint32_t d_conv = tmem_base + as * kRtN;
       const uint32_t d_lff = tmem_base + kRtLffCol0 + lb * kRtN;
-      for (int c = 0; c < kRtChunks; ++c, ++it) {
-        mbar_wait(&ctrl->full[s], ph);                                 // both warps observe every phase
-        if ((it & 1u) == Y) {
-          if (tl == 0) mbar_wait(&ctrl->wfull[c], 0);
-          wait_turn(it);
-          const uint32_t a_lo = ((smem_u32(stage0 + (size_t)s * kRtABytes) >> 4) & 0x3FFFu) | A_LBO;
-          const uint32_t b_lo = ((smem_u32(res_w + c * kRtWChunk) >> 4) & 0x3FFFu) | B_LBO;
+      for (int c = 0; c < kRtChunks; ++c, ++sit) {
+        if ((uint32_t)(c & 1) == Y) {
+          const uint32_t a_lo = stage_lo + s * (kRtABytes >> 4);
+          const uint32_t b_lo = w_lo + c * (kRtWChunk >> 4);
           const uint32_t first = (c == 0) ? 0u : 1u;
+          if (Y == 0 && lane == 0) rt_rec(p, 1, dit, 0);
+          mbar_wait(&ctrl->full[s], ph);
+          if (Y == 0 && lane == 0) rt_rec(p, 1, dit, 1);
+          if (tl == 0) mbar_wait(&ctrl->wfull[c], 0);
+          wait_turn(sit);
+          if (Y == 0 && lane == 0) rt_rec(p, 1, dit, 2);
           if (elect_one()) {
+            // same order per accumulator as conv_igemm.cu (ky outer, k16 step inner): fused and layer-by-layer results
+            // are bit-identical
 #pragma unroll
-            for (int jj = 0; jj < kKC / 16; ++jj) {
-              const uint32_t a_k = a_lo + jj * 2 * (kRtAPlane >> 4);
-              const uint32_t b_k = b_lo + jj * 2 * kRtN;
+            for (int ky = 0; ky < 3; ++ky) {                           // conv: A shifted by ky rows, B = slab ky
 #pragma unroll
-              for (int ky = 0; ky < 3; ++ky) {                         // conv: A shifted by ky rows, B = slab ky
-                const uint64_t ad = ((uint64_t)D_HI << 32) | (a_k + ky * kTWH);
-                const uint64_t bd = ((uint64_t)D_HI << 32) | (b_k + ky * (kRtSlab >> 4));
+              for (int jj = 0; jj < kKC / 16; ++jj) {
+                const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + jj * 2 * (kRtAPlane >> 4) + ky * kTWH);
+                const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + jj * 2 * kRtN + ky * (kRtSlab >> 4));
                 umma_f16_ss(d_conv, ad, bd, idesc, (jj == 0 && ky == 0) ? first : 1u);
               }
-              {                                                        // LFF: centre tap (ky = 1, kx = 1), B = slab 3
-                const uint64_t ad = ((uint64_t)D_HI << 32) | (a_k + kTWH + 1);
-                const uint64_t bd = ((uint64_t)D_HI << 32) | (b_k + 3 * (kRtSlab >> 4));
-                umma_f16_ss(d_lff, ad, bd, idesc, jj == 0 ? first : 1u);
+              if (ky == 1) {                                           // LFF: centre tap (ky = 1, kx = 1), B = slab 3
+#pragma unroll
+                for (int jj = 0; jj < kKC / 16; ++jj) {
+                  const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + jj * 2 * (kRtAPlane >> 4) + kTWH + (ALIGNED ? 0 : 1));
+                  const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + jj * 2 * kRtN + 3 * (kRtSlab >> 4));
+                  umma_f16_ss(d_lff, ad, bd, idesc, jj == 0 ? first : 1u);
+                }
               }
             }
             umma_commit(&ctrl->empty[s]);                              // frees the smem stage once these MMAs retire
           }
           __syncwarp();
-          pass_turn(it);
+          pass_turn(sit);
+          if (Y == 0 && lane == 0) rt_rec(p, 1, dit, 3);
+          ++dit;
         }
         if (++s == kRtStages) { s = 0; ph ^= 1; }
       }
       if (elect_one()) umma_commit(&ctrl->conv_full[as]);              // this warp's share of the tile's conv MMAs
       __syncwarp();
-      if (tl > 0) tail_item(tl - 1);
+      if (Y == 1 && tl > 0) tail_item(tl - 1);
     }
-    if (tl > 0) tail_item(tl - 1);
+    if (Y == 1 && tl > 0) tail_item(tl - 1);
   } else if (warp >= 4 && warp < 8) {
     // ========================================================== epilogue A: conv accumulator -> g3 tile (smem)
     const int q = warp & 3;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tl) {
       const uint32_t as = tl & 1, uph = (tl >> 1) & 1;
+      if (warp == 4 && lane == 0) rt_rec(p, 2, tl, 0);
       mbar_wait(&ctrl->conv_full[as], uph);
+      if (warp == 4 && lane == 0) rt_rec(p, 2, tl, 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kRtN;
       uint32_t v[96];
@@ -269,12 +303,16 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
         }
         ow[i >> 1] = rt_pack_h2(f[0], f[1]);
       }
+      if (warp == 4 && lane == 0) rt_rec(p, 2, tl, 2);
       mbar_wait(&ctrl->h_empty[as], uph ^ 1);                          // tail of tile tl-2 has consumed this buffer
-      uint8_t* h = htile + as * kRtHBytes + (q * 32 + lane) * 16;
+      uint8_t* h = htile + as * kRtHBytes + (q * 32 + lane + (ALIGNED ? 1 : 0)) * 16;
+      if (!ALIGNED || lane < 31) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(h + k * kRtHPlane) = o[k];
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(h + k * kRtHPlane) = o[k];
+      }
       fence_proxy_async();                                             // generic-proxy stores -> visible to tcgen05.mma
       mbar_arrive(&ctrl->h_full[as]);
+      if (warp == 4 && lane == 0) rt_rec(p, 2, tl, 3);
     }
   } else if (warp >= 8) {
     // ========================================================== epilogue B: LFF accumulator + bias + x -> x'
@@ -294,7 +332,9 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
         const size_t off = ((((size_t)b * p.res_planes + p.res_plane0 + k) * p.H + y) * p.W + x) * 8;
         rbuf[k] = valid ? *reinterpret_cast<const uint4*>(p.res + off) : make_uint4(0, 0, 0, 0);
       }
+      if (warp == 8 && lane == 0) rt_rec(p, 0, tl, 2);
       mbar_wait(&ctrl->lff_full[lb], (tl / 3) & 1);
+      if (warp == 8 && lane == 0) rt_rec(p, 0, tl, 3);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kRtLffCol0 + lb * kRtN;
 #pragma unroll
@@ -306,6 +346,10 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
         if (g0 == 48) {                                                // all 96 columns are in registers
           tc_fence_before();
           mbar_arrive(&ctrl->lff_empty[lb]);
+        }
+        if constexpr (ALIGNED) {                                       // accumulator row p holds output pixel p-1
+#pragma unroll
+          for (int j = 0; j < 48; ++j) v[j] = __shfl_down_sync(0xffffffffu, v[j], 1);
         }
         if (valid) {
 #pragma unroll
@@ -366,9 +410,19 @@ int launch_rdb_tail(const bin_act_t& x, int x_plane0, const bin_act_t& g, int g_
   p.ntiles = nb * p.tiles_x * p.tiles_y;
   p.out = reinterpret_cast<__half*>(out.ptr); p.out_planes = out.planes; p.out_plane0 = out_plane0;
   p.res = reinterpret_cast<const __half*>(x.ptr); p.res_planes = x.planes; p.res_plane0 = x_plane0;
+  const char* ea = getenv("BIN_B200_TAIL_ALIGNED");
+  const bool aligned = !(ea && *ea == '0');
+  { const char* e = getenv("BIN_B200_DEBUG"); p.debug = (e && *e) ? atoi(e) : 0; }   // perf experiments only
+  if (p.debug & 8) {
+    if (!g_dbg) { BIN_CUDA_OK(cudaMalloc(&g_dbg, 3 * 4096 * sizeof(long long))); }
+    BIN_CUDA_OK(cudaMemsetAsync(g_dbg, 0, 3 * 4096 * sizeof(long long), s));
+    p.dbg = g_dbg;
+  }
+  auto kern = aligned ? rdb_tail_kernel<true> : rdb_tail_kernel<false>;
   static bool attr_done = false;
   if (!attr_done) {
-    BIN_CUDA_OK(cudaFuncSetAttribute(rdb_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem));
+    BIN_CUDA_OK(cudaFuncSetAttribute(rdb_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem));
+    BIN_CUDA_OK(cudaFuncSetAttribute(rdb_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem));
     attr_done = true;
   }
   static int sms = []() {
@@ -378,7 +432,7 @@ int launch_rdb_tail(const bin_act_t& x, int x_plane0, const bin_act_t& g, int g_
     return v > 0 ? v : 148;
   }();
   const int grid = p.ntiles < sms ? p.ntiles : sms;
-  rdb_tail_kernel<<<grid, 384, kRtSmem, s>>>(p);
+  kern<<<grid, 384, kRtSmem, s>>>(p);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
 }

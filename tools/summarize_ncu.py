@@ -19,7 +19,7 @@ def short(name):
     if m:
         epi = {"0": "P8", "1": "PIXSHUF", "2": "FINAL"}[m.group(3)]
         return f"conv_igemm<NT={m.group(1)},KS={m.group(2)},{epi},SX={m.group(4)}>"
-    return re.sub(r"\(.*", "", name).replace("binb::", "")
+    return re.sub(r"\(.*", "", name).replace("binb::", "").replace("void ", "")
 
 
 def launches():
@@ -40,8 +40,8 @@ def launches():
         tot += v
     with open(os.path.join(P, f"{tag}_launches_window.md"), "w") as f:
         f.write(f"# {tag}: ncu launch list of ONE steady-state 6-frame 1280x720 window\n\n"
-                "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 802 -c 274 --csv python tools/run_window.py 2`\n"
-                "(BIN_B200_GRAPH=0; skip = 528 weight-pack launches + the 274 launches of window 0). Per-launch times under ncu are\n"
+                f"Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s {528 + len(rows)} -c {len(rows)} --csv python tools/run_window.py 2`\n"
+                f"(BIN_B200_GRAPH=0; skip = 528 weight-pack launches + the {len(rows)} launches of window 0). Per-launch times under ncu are\n"
                 "cold-cache and serialised: compare SHARES, not absolutes.\n\n"
                 f"launches: {len(rows)}, sum of kernel durations: {tot/1e3:.2f} ms\n\n| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -86,3 +86,7 @@ full("prof_wgrad.ncu-rep", "ncu --set full: weight-gradient GEMM (tcgen05 MN-maj
      "Command: `BT_STEPS=1 BT_WARM=1 ncu --set full --clock-control none --import-source on -k regex:wgrad_kernel -s 300 -c 2 python tools/bench_train.py 4 256 256` (captured before the slab-reduce flush replaced the atomics).")
 full("prof_tail.ncu-rep", "ncu --set full: tail of the same stage: GFF.0, GFF.1, UPNet.0(+PixelShuffle), UPNet.2(+mean)",
      "Command: `ncu --set full --clock-control none --import-source on -k regex:conv_igemm_kernel -s 392 -c 4 python tools/run_window.py 2`.")
+full("prof_rdb_tail.ncu-rep", "ncu --set full: fused RDB tail (conv3 3x3+ReLU, LFF 1x1, residual) of the stage-1 launch (5 batched calls, 360x640)",
+     "Command: `ncu --set full --clock-control none --import-source on -k regex:rdb_tail_kernel -s 48 -c 2 python tools/run_window.py 2`.\n"
+     "Algorithmic bytes per launch: reads 5*230400*384 B (x + g0..g2) + 5*230400*192 B (residual, L2-resident), writes 5*230400*192 B.\n"
+     "Algorithmic FLOPs per launch: 2*5*230400*(192*32*9 + 224*96).")
