@@ -160,38 +160,60 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def _time_ms(torch, fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def dominant_kernel_roofline(torch, ops, pk, ncalls, h, w):
-    """conv_igemm_kernel<32,3,P8,SX> (the x-stacked RDB conv, 70 % of window FLOPs) timed alone with
-    CUDA events at the exact shapes the window launches it with (B = batched calls)."""
+    """conv_igemm_kernel<32,3,P8,SX> (the x-stacked RDB convs 0..2, 43 % of the window's kernel time; the 4th conv runs
+    inside the fused tail kernel) timed alone with CUDA events at the exact shapes the window launches it with
+    (B = batched calls).  Also times the second-largest kernel, the fused RDB tail, against the HBM roofline."""
     dev = "cuda"
     tot_flops = tot_ms = 0.0
-    for c in range(4):
+    x = torch.randn(ncalls, 12, h, w, 8, device=dev).half()
+    g = torch.randn(ncalls, 16, h, w, 8, device=dev).half()
+    for c in range(3):
         cin = 96 + 32 * c
         wt = torch.randn(32, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
         wp, bp = ops.pack_conv_weight(wt, 32, cin), ops.pad_bias(torch.zeros(32, device=dev), 32)
-        x = torch.randn(ncalls, 12, h, w, 8, device=dev).half()
-        g = torch.randn(ncalls, 16, h, w, 8, device=dev).half()
         kw = dict(in0_planes=12, in1=g, in1_planes=4 * c, relu=True, out=g, out_plane0=4 * c)
-        for _ in range(3):
-            ops.conv_fwd(x, wp, bp, 3, 32, **kw)
-        torch.cuda.synchronize()
-        reps = 10
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            ops.conv_fwd(x, wp, bp, 3, 32, **kw)
-        e1.record()
-        torch.cuda.synchronize()
-        tot_ms += e0.elapsed_time(e1) / reps
+        tot_ms += _time_ms(torch, lambda: ops.conv_fwd(x, wp, bp, 3, 32, **kw))
         tot_flops += 2.0 * ncalls * h * w * cin * 32 * 9
     ach = tot_flops / (tot_ms * 1e-3) / 1e12
     peak = pk["bf16_tflops"]
-    return {"bound": "tensor", "kernel": "conv_igemm_kernel<32,3,P8,SX> (RDB 3x3 convs, 4 shapes)", "achieved": ach,
+    # fused tail: conv3 (192 -> 32, 3x3, ReLU) + LFF (224 -> 96, 1x1) + residual; HBM sees x + g0..g2 in, x' out
+    w3 = ops.pack_conv_weight(torch.randn(32, 192, 3, 3, device=dev) / 1728 ** 0.5, 32, 192)
+    wl = ops.pack_conv_weight(torch.randn(96, 224, 1, 1, device=dev) / 224 ** 0.5, 96, 224)
+    b3, bl = ops.pad_bias(torch.zeros(32, device=dev), 32), ops.pad_bias(torch.zeros(96, device=dev), 96)
+    out = torch.empty(ncalls, 12, h, w, 8, device=dev).half()
+    tail_ms = _time_ms(torch, lambda: ops.rdb_tail_fwd(x, g, w3, b3, wl, bl, out))
+    tail_bytes = ncalls * h * w * (384 + 192)
+    tail_flops = 2.0 * ncalls * h * w * (192 * 32 * 9 + 224 * 96)
+    hbm = pk["hbm_gbs"]
+    tail = {"bound": "hbm", "kernel": "rdb_tail_kernel (conv3 + LFF + residual fused; 32 % of the window's kernel time)",
+            "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+            "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / hbm,
+            "traffic": 6.386e8 if (ncalls, h, w) == (5, 360, 640) else None,
+            "traffic_note": "dram__bytes_read+write of one launch (profiles/r01b_prof_rdb_tail.md); algorithmic bytes "
+                            f"{tail_bytes:.4g} (576 B/position: 192 input channels in, 96 out; the residual re-read hits L2)",
+            "tflops": tail_flops / (tail_ms * 1e-3) / 1e12, "ms_per_launch": tail_ms,
+            "note": "bound by neither roof: 150 KB of resident weights leave a 4 x 12 KB activation ring, the kernel runs "
+                    "at the ring's latency (DESIGN.md 5d)"}
+    return {"bound": "tensor", "kernel": "conv_igemm_kernel<32,3,P8,SX> (RDB 3x3 convs 0..2, 3 shapes)", "achieved": ach,
             "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "traffic": 1.5609e9 if (ncalls, h, w) == (5, 360, 640) else None,
-            "traffic_note": "dram__bytes_read+write summed over the 4 launches (profiles/r01_prof_rdb5.md); algorithmic bytes 1.622e9",
+            "traffic": 1.0537e9 if (ncalls, h, w) == (5, 360, 640) else None,
+            "traffic_note": "dram__bytes_read+write summed over the 3 launches (profiles/r01_prof_rdb5.md); algorithmic bytes 1.106e9",
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({pk['source']}, burst: kernel timed alone)",
-            "algorithmic_flops_per_launch_set": tot_flops, "ms_per_launch_set": tot_ms}
+            "algorithmic_flops_per_launch_set": tot_flops, "ms_per_launch_set": tot_ms, "second_kernel": tail}
 
 
 def run_ours(args):
@@ -322,8 +344,8 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 6 * 3 * H * W * 4, "d2h_bytes_per_step": 3 * 3 * H * W * 4,
                     "note": "WindowPipeline: pinned-host frames in, outputs 13,8,12 (test.py:380-402) back to pinned host, copies overlapped with the previous/next window",
                     "matches_device_result": e2e_ok},
-            "gpu_launches": args.steps * 274 * 2,
-            "gpu_launches_note": "per window: 4 batched backbone stages x (1 pack + 66 conv) + 6 ConvLSTM = 274 kernels (replayed as one CUDA graph); timed twice (value, e2e)",
+            "gpu_launches": args.steps * 226 * 2,
+            "gpu_launches_note": "per window: 4 batched backbone stages x (1 pack + 42 conv + 12 fused RDB tails) + 6 ConvLSTM = 226 kernels (replayed as one CUDA graph); timed twice (value, e2e)",
             "roofline": roof,
             "cpu_baseline": {"value": 1.0 / (cpu_dt * cpu_scale), "unit": UNIT, "cores": cpu_threads, "kind": "port",
                              "sample": f"128x128 6-frame window on the fp32 CPU oracle, mean of 3 ({cpu_dt:.2f} s each), scaled x{cpu_scale:.2f} by pixel count to {W}x{H}"},

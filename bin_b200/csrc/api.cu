@@ -751,6 +751,14 @@ int bin_pyramid3_fwd(const bin_net_t* net, const float* const* F, float* const* 
   return run_stage(net, 2, 5, {{{o[3], F[1], o[3], o[4], F[2]}, o[5]}}, B, H, W, workspace, workspace_bytes, s);
 }
 
+int bin_rdb_tail_fwd(const bin_act_t* x, int x_plane0, const bin_act_t* g, int g_plane0, const void* w_conv,
+                     const float* b_conv, const void* w_lff, const float* b_lff, const bin_act_t* out, int out_plane0,
+                     int b_begin, int b_count, int y_begin, int y_count, bin_stream_t s) {
+  if (!x || !g || !out || !x->ptr || !g->ptr || !out->ptr || !w_conv || !b_conv || !w_lff || !b_lff)
+    return fail(BIN_ERR_ARG, "rdb_tail_fwd: null argument");
+  return launch_rdb_tail(*x, x_plane0, *g, g_plane0, w_conv, b_conv, w_lff, b_lff, *out, out_plane0, b_begin, b_count,
+                         y_begin, y_count, (cudaStream_t)s);
+}
 int bin_adam_step(const bin_adam_tensor_t* table_dev, const int* chunk_prefix_dev, int ntensors, int nchunks, float lr,
                   float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
                   float bias_correction2, float grad_scale, bin_stream_t s) {

@@ -125,6 +125,14 @@ def conv_fwd(in0: torch.Tensor, w_packed: torch.Tensor, bias_pad: torch.Tensor, 
     check(lib().bin_conv_fwd(C.byref(a), _stream()))
 
 
+def rdb_tail_fwd(x: torch.Tensor, g: torch.Tensor, w_conv: torch.Tensor, b_conv: torch.Tensor, w_lff: torch.Tensor,
+                 b_lff: torch.Tensor, out: torch.Tensor, *, x_plane0: int = 0, g_plane0: int = 0, out_plane0: int = 0,
+                 sub=(0, 0, 0, 0)) -> None:
+    """Fused conv3 + LFF + residual of one RDB (RDN.py:141-147, 162-165) on P8 tensors; see bin_rdb_tail_fwd."""
+    ax, ag, ao = act_view(x), act_view(g), act_view(out)
+    check(lib().bin_rdb_tail_fwd(C.byref(ax), x_plane0, C.byref(ag), g_plane0, w_conv.data_ptr(), b_conv.data_ptr(),
+                                 w_lff.data_ptr(), b_lff.data_ptr(), C.byref(ao), out_plane0, *sub, _stream()))
+
 def convlstm_fwd(x, w, b, state=None):
     """ConvLSTMCell.forward (RDN.py:50-95) -> (h, c)."""
     x = _req(x, torch.float32, "x")

@@ -115,6 +115,15 @@ typedef struct {
 } bin_conv_args_t;
 int bin_conv_fwd(const bin_conv_args_t* a, bin_stream_t s);
 
+/* Fused tail of one RDB (RDN.py:141-147 for the 4th RDB_Conv, :162-165): g3 = ReLU(conv3x3(cat(x, g0..g2))) and
+ * out = LFF(cat(x, g0..g3)) + x in one kernel; g3 is never written.  x: 12 planes from x_plane0, g: the 12 planes of
+ * g0..g2 from g_plane0, out: 12 planes from out_plane0 (may be other planes of x's tensor).  w_conv / w_lff are the
+ * bin_pack_conv_weight outputs of the (32,192,3,3) conv (variant BIN_CONV_DEFAULT) and the (96,224,1,1) LFF; b_conv
+ * has 32 floats, b_lff 96.  b/y sub-ranges as in the conv arguments: a count of 0 means "to the end".  fp16 mode only. */
+int bin_rdb_tail_fwd(const bin_act_t* x, int x_plane0, const bin_act_t* g, int g_plane0, const void* w_conv,
+                     const float* b_conv, const void* w_lff, const float* b_lff, const bin_act_t* out, int out_plane0,
+                     int b_begin, int b_count, int y_begin, int y_count, bin_stream_t s);
+
 /* Data-gradient weights of a conv (cout,cin,k): V[ci][co][ky][kx] = W[co][row0+ci][k-1-ky][k-1-kx] for ci < nrows,
  * packed like a forward conv with Cout' = cout_pad_t (multiple of 96), Cin' = cin_pad_t (multiple of 32):
  * bin_conv_fwd over dY with these weights gives dX[:, row0:row0+nrows]. */
