@@ -82,6 +82,33 @@ def test_rdb_shapes_vs_oracle(net, sd, B, H, W):
     assert torch.isfinite(y).all()
     assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
 
+@pytest.mark.parametrize("B,H,W,sub", [(2, 9, 37, (0, 0, 0, 0)), (3, 16, 64, (1, 2, 4, 7)), (1, 4, 30, (0, 1, 0, 4)), (1, 70, 45, (0, 0, 3, 0))])
+def test_rdb_tail_bit_identical_to_layerwise(B, H, W, sub):
+    """bin_rdb_tail_fwd == conv3 (x-stacked kernel) followed by the LFF kernel, bit for bit (same accumulation order),
+    on full tensors and on batch / row sub-ranges (rows outside the range must stay untouched)."""
+    from bin_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(B * 1000 + H * 10 + W)
+    rnd = lambda *sh: torch.randn(*sh, device="cuda", generator=gen)
+    x, g = rnd(B, 12, H, W, 8).half(), rnd(B, 16, H, W, 8).half()
+    w3, wl = rnd(32, 192, 3, 3) / 1728 ** 0.5, rnd(96, 224, 1, 1) / 224 ** 0.5
+    b3, bl = ops.pad_bias(rnd(32) * 0.1, 32), ops.pad_bias(rnd(96) * 0.1, 96)
+    p3, pl = ops.pack_conv_weight(w3, 32, 192), ops.pack_conv_weight(wl, 96, 224)
+    g_ref = g.clone()
+    sentinel = torch.full((B, 12, H, W, 8), 7.0, device="cuda").half()
+    out_ref, out = sentinel.clone(), sentinel.clone()
+    s4 = None if sub == (0, 0, 0, 0) else sub
+    ops.conv_fwd(x, p3, b3, 3, 32, in0_planes=12, in1=g_ref, in1_planes=12, relu=True, out=g_ref, out_plane0=12, sub=s4)
+    ops.conv_fwd(x, pl, bl, 1, 96, in0_planes=12, in1=g_ref, in1_planes=16, out=out_ref, res=x, sub=s4)
+    ops.rdb_tail_fwd(x, g, p3, b3, pl, bl, out, sub=sub)
+    torch.cuda.synchronize()
+    assert torch.equal(g[:, :12], g_ref[:, :12])                    # inputs untouched, g3 never written
+    assert torch.equal(out, out_ref)
+    b0, nb, y0, ny = sub
+    rows = torch.zeros(B, H, dtype=torch.bool)
+    rows[b0:(b0 + nb) if nb else B, y0:(y0 + ny) if ny else H] = True
+    written = (out != sentinel).any(dim=(1, 3, 4)).cpu()
+    assert not (written & ~rows).any()
+
 @pytest.mark.parametrize("name,n", [("model1_1", 2), ("model2_1", 3), ("model3_1", 5), ("model4_1", 5)])
 def test_backbone_golden(golden_dir, net, name, n):
     g = _load(golden_dir, f"backbone_{name}.npz")
