@@ -90,11 +90,16 @@ __device__ __forceinline__ float2 rt_unpack_h2(uint32_t u) {
   return __half22float2(h);
 }
 
-// ALIGNED: the LFF's centre tap reads the A tile at the x-unshifted start (row offset 32, 512-byte aligned) like the
-// x-stacked conv taps, so its accumulator row p holds output pixel p-1: the g3 tile is stored one row down and epilogue B
-// takes its values from lane+1.  !ALIGNED shifts the descriptor start by one 16-byte row instead (no shuffles, but
-// every 8-row core matrix of that operand then straddles two 128-byte shared-memory lines).
-template <bool ALIGNED>
+// The LFF's centre tap reads the A tile at the x-unshifted start (row offset 32, 512-byte aligned) like the x-stacked
+// conv taps, so its accumulator row p holds output pixel p-1: the g3 tile is stored one row down and epilogue B takes
+// its values from lane+1.  (Shifting the descriptor start by one 16-byte row instead -- no shuffles, but every 8-row
+// core matrix of that operand then straddles two 128-byte shared-memory lines -- measured 1 % slower.)
+//
+// STREAMS: even and odd tiles of a CTA form two independent instruction streams (producer + MMA warp + two ring slots +
+// one conv accumulator each) that share the tensor pipe, the LFF accumulators and the epilogue warps; nothing orders
+// one stream against the other, so one stream's barrier polls and its wait for the g3 tile are covered by the other's
+// MMAs.  !STREAMS: the two MMA warps alternate the items of ONE tile stream through a hand-off counter.
+template <bool STREAMS>
 __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant__ RdbTailParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   RtCtrl* ctrl = reinterpret_cast<RtCtrl*>(smem);
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
     for (int i = 0; i < kRtStages; ++i) { mbar_init(&ctrl->full[i], 1); mbar_init(&ctrl->empty[i], 1); }
     for (int i = 0; i <= kRtChunks; ++i) mbar_init(&ctrl->wfull[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&ctrl->conv_full[i], 2);       // one tcgen05.commit per MMA warp
+      mbar_init(&ctrl->conv_full[i], STREAMS ? 1 : 2);   // tcgen05.commit of the stream's / of each MMA warp
       mbar_init(&ctrl->conv_empty[i], 128);    // the four epilogue-A warps
       mbar_init(&ctrl->h_full[i], 128);
       mbar_init(&ctrl->h_empty[i], 1);
@@ -136,31 +141,36 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
 
-  if (warp == 0 && lane == 0) {
-    // ========================================================== TMA producer
-    for (int c = 0; c < kRtChunks; ++c) {
-      mbar_expect_tx(&ctrl->wfull[c], kRtWChunk);
-      bulk_load_1d(res_w + c * kRtWChunk, p.w_conv + (size_t)c * 3 * kRtSlab, 3 * kRtSlab, &ctrl->wfull[c]);
-      bulk_load_1d(res_w + c * kRtWChunk + 3 * kRtSlab, p.w_lff + (size_t)c * kRtSlab, kRtSlab, &ctrl->wfull[c]);
+  if ((warp == 0 || (STREAMS && warp == 2)) && lane == 0) {
+    // ========================================================== TMA producer(s)
+    const uint32_t Y = warp >> 1;
+    if (Y == 0) {
+      for (int c = 0; c < kRtChunks; ++c) {
+        mbar_expect_tx(&ctrl->wfull[c], kRtWChunk);
+        bulk_load_1d(res_w + c * kRtWChunk, p.w_conv + (size_t)c * 3 * kRtSlab, 3 * kRtSlab, &ctrl->wfull[c]);
+        bulk_load_1d(res_w + c * kRtWChunk + 3 * kRtSlab, p.w_lff + (size_t)c * kRtSlab, kRtSlab, &ctrl->wfull[c]);
+      }
+      mbar_expect_tx(&ctrl->wfull[kRtChunks], kRtSlab);
+      bulk_load_1d(res_w + kRtChunks * kRtWChunk, p.w_lff + (size_t)kRtChunks * kRtSlab, kRtSlab, &ctrl->wfull[kRtChunks]);
     }
-    mbar_expect_tx(&ctrl->wfull[kRtChunks], kRtSlab);
-    bulk_load_1d(res_w + kRtChunks * kRtWChunk, p.w_lff + (size_t)kRtChunks * kRtSlab, kRtSlab, &ctrl->wfull[kRtChunks]);
-    uint32_t s = 0, ph = 0, pit = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      int t = tile;
+    // STREAMS: stream Y loads tiles Y, Y+2, ... into ring slots Y and Y+2; else one producer fills slots 0..3 in turn
+    uint32_t k = 0;
+    for (uint32_t tl = STREAMS ? Y : 0; (int)(blockIdx.x + tl * gridDim.x) < p.ntiles; tl += STREAMS ? 2 : 1) {
+      int t = blockIdx.x + tl * gridDim.x;
       const int txi = t % p.tiles_x; t /= p.tiles_x;
       const int tyi = t % p.tiles_y;
       const int b = p.b0 + t / p.tiles_y;
       const int x0 = txi * kRtTW - 1, y0 = p.y0 + tyi * kRtTH - 1;
-      for (int c = 0; c < kRtChunks; ++c, ++pit) {
-        rt_rec(p, 0, pit, 0);
-        mbar_wait(&ctrl->empty[s], ph ^ 1);
-        rt_rec(p, 0, pit, 1);
-        mbar_expect_tx(&ctrl->full[s], kRtABytes);
+      for (int c = 0; c < kRtChunks; ++c, ++k) {
+        const uint32_t slot = STREAMS ? Y + 2 * (k & 1) : k % kRtStages;
+        const uint32_t par = STREAMS ? (k >> 1) & 1 : (k / kRtStages) & 1;
+        if (Y == 0) rt_rec(p, 0, k, 0);
+        mbar_wait(&ctrl->empty[slot], par ^ 1);
+        if (Y == 0) rt_rec(p, 0, k, 1);
+        mbar_expect_tx(&ctrl->full[slot], kRtABytes);
         const bool seg1 = c >= 3;
-        tma_load_4d(stage0 + (size_t)s * kRtABytes, seg1 ? (const void*)&p.tmap1 : (const void*)&p.tmap0, &ctrl->full[s],
-                    x0 * 8, y0, seg1 ? p.plane0_1 + (c - 3) * kKPL : p.plane0_0 + c * kKPL, b);
-        if (++s == kRtStages) { s = 0; ph ^= 1; }
+        tma_load_4d(stage0 + (size_t)slot * kRtABytes, seg1 ? (const void*)&p.tmap1 : (const void*)&p.tmap0,
+                    &ctrl->full[slot], x0 * 8, y0, seg1 ? p.plane0_1 + (c - 3) * kKPL : p.plane0_0 + c * kKPL, b);
       }
     }
   } else if (warp == 1 || warp == 3) {
@@ -203,7 +213,7 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
       const uint32_t b_lo = ((smem_u32(res_w + kRtChunks * kRtWChunk) >> 4) & 0x3FFFu) | B_LBO;
       const uint32_t d = tmem_base + kRtLffCol0 + plb * kRtN;
       mbar_wait(&ctrl->h_full[hb], (pt >> 1) & 1);
-      if (pt == 0) mbar_wait(&ctrl->wfull[kRtChunks], 0);
+      if (pt < 2) mbar_wait(&ctrl->wfull[kRtChunks], 0);              // first tail of either MMA warp
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -219,6 +229,58 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
     };
     const uint32_t stage_lo = ((smem_u32(stage0) >> 4) & 0x3FFFu) | A_LBO;
     const uint32_t w_lo = ((smem_u32(res_w) >> 4) & 0x3FFFu) | B_LBO;
+    // one stage item: 3 x 2 conv MMAs + 2 LFF MMAs on ring slot `slot`, chunk c
+    auto issue_item = [&](uint32_t slot, int c, uint32_t d_conv, uint32_t d_lff, bool last, uint32_t as) {
+      const uint32_t a_lo = stage_lo + slot * (kRtABytes >> 4);
+      const uint32_t b_lo = w_lo + c * (kRtWChunk >> 4);
+      const uint32_t first = (c == 0) ? 0u : 1u;
+      if (elect_one()) {
+        // same order per accumulator as conv_igemm.cu (ky outer, k16 step inner): fused and layer-by-layer results
+        // are bit-identical
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {                               // conv: A shifted by ky rows, B = slab ky
+#pragma unroll
+          for (int jj = 0; jj < kKC / 16; ++jj) {
+            const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + jj * 2 * (kRtAPlane >> 4) + ky * kTWH);
+            const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + jj * 2 * kRtN + ky * (kRtSlab >> 4));
+            umma_f16_ss(d_conv, ad, bd, idesc, (jj == 0 && ky == 0) ? first : 1u);
+          }
+          if (ky == 1) {                                               // LFF: centre row, x-unshifted start, B = slab 3
+#pragma unroll
+            for (int jj = 0; jj < kKC / 16; ++jj) {
+              const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + jj * 2 * (kRtAPlane >> 4) + kTWH);
+              const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + jj * 2 * kRtN + 3 * (kRtSlab >> 4));
+              umma_f16_ss(d_lff, ad, bd, idesc, jj == 0 ? first : 1u);
+            }
+          }
+        }
+        umma_commit(&ctrl->empty[slot]);                               // frees the smem slot once these MMAs retire
+        if (last) umma_commit(&ctrl->conv_full[as]);
+      }
+      __syncwarp();
+    };
+    if constexpr (STREAMS) {
+      uint32_t k = 0, n = 0;
+      for (uint32_t tl2 = Y; (int)(blockIdx.x + tl2 * gridDim.x) < p.ntiles; tl2 += 2, ++n) {
+        const uint32_t lb = tl2 % 3;
+        // conv[Y] is free: this warp waited for the g3 tile of its previous tile, which epilogue A writes after it
+        // has read the accumulator.  The rotating LFF accumulator was released three tiles ago.
+        mbar_wait(&ctrl->lff_empty[lb], ((tl2 / 3) & 1) ^ 1);
+        const uint32_t d_conv = tmem_base + Y * kRtN;
+        const uint32_t d_lff = tmem_base + kRtLffCol0 + lb * kRtN;
+        for (int c = 0; c < kRtChunks; ++c, ++k) {
+          const uint32_t slot = Y + 2 * (k & 1);
+          if (Y == 0 && lane == 0) rt_rec(p, 1, k, 0);
+          mbar_wait(&ctrl->full[slot], (k >> 1) & 1);
+          if (n == 0) mbar_wait(&ctrl->wfull[c], 0);
+          tc_fence_after();
+          if (Y == 0 && lane == 0) rt_rec(p, 1, k, 1);
+          issue_item(slot, c, d_conv, d_lff, c == kRtChunks - 1, Y);
+          if (Y == 0 && lane == 0) rt_rec(p, 1, k, 3);
+        }
+        tail_item(tl2);                                                // waits for this tile's g3, then 2 MMAs
+      }
+    } else
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tl) {
       const uint32_t as = tl & 1, lb = tl % 3;
       if (Y == 0) {
@@ -252,7 +314,7 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
               if (ky == 1) {                                           // LFF: centre tap (ky = 1, kx = 1), B = slab 3
 #pragma unroll
                 for (int jj = 0; jj < kKC / 16; ++jj) {
-                  const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + jj * 2 * (kRtAPlane >> 4) + kTWH + (ALIGNED ? 0 : 1));
+                  const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + jj * 2 * (kRtAPlane >> 4) + kTWH + 0);
                   const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + jj * 2 * kRtN + 3 * (kRtSlab >> 4));
                   umma_f16_ss(d_lff, ad, bd, idesc, jj == 0 ? first : 1u);
                 }
@@ -271,7 +333,7 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
       __syncwarp();
       if (Y == 1 && tl > 0) tail_item(tl - 1);
     }
-    if (Y == 1 && tl > 0) tail_item(tl - 1);
+    if (!STREAMS && Y == 1 && tl > 0) tail_item(tl - 1);
   } else if (warp >= 4 && warp < 8) {
     // ========================================================== epilogue A: conv accumulator -> g3 tile (smem)
     const int q = warp & 3;
@@ -305,8 +367,8 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
       }
       if (warp == 4 && lane == 0) rt_rec(p, 2, tl, 2);
       mbar_wait(&ctrl->h_empty[as], uph ^ 1);                          // tail of tile tl-2 has consumed this buffer
-      uint8_t* h = htile + as * kRtHBytes + (q * 32 + lane + (ALIGNED ? 1 : 0)) * 16;
-      if (!ALIGNED || lane < 31) {
+      uint8_t* h = htile + as * kRtHBytes + (q * 32 + lane + 1) * 16;
+      if (lane < 31) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(h + k * kRtHPlane) = o[k];
       }
@@ -347,10 +409,8 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
           tc_fence_before();
           mbar_arrive(&ctrl->lff_empty[lb]);
         }
-        if constexpr (ALIGNED) {                                       // accumulator row p holds output pixel p-1
 #pragma unroll
-          for (int j = 0; j < 48; ++j) v[j] = __shfl_down_sync(0xffffffffu, v[j], 1);
-        }
+        for (int j = 0; j < 48; ++j) v[j] = __shfl_down_sync(0xffffffffu, v[j], 1);   // accumulator row p holds pixel p-1
         if (valid) {
 #pragma unroll
           for (int k = 0; k < 6; ++k) {
@@ -410,15 +470,15 @@ int launch_rdb_tail(const bin_act_t& x, int x_plane0, const bin_act_t& g, int g_
   p.ntiles = nb * p.tiles_x * p.tiles_y;
   p.out = reinterpret_cast<__half*>(out.ptr); p.out_planes = out.planes; p.out_plane0 = out_plane0;
   p.res = reinterpret_cast<const __half*>(x.ptr); p.res_planes = x.planes; p.res_plane0 = x_plane0;
-  const char* ea = getenv("BIN_B200_TAIL_ALIGNED");
-  const bool aligned = !(ea && *ea == '0');
+  const char* ea = getenv("BIN_B200_TAIL_STREAMS");
+  const bool streams = !(ea && *ea == '0');
   { const char* e = getenv("BIN_B200_DEBUG"); p.debug = (e && *e) ? atoi(e) : 0; }   // perf experiments only
   if (p.debug & 8) {
     if (!g_dbg) { BIN_CUDA_OK(cudaMalloc(&g_dbg, 3 * 4096 * sizeof(long long))); }
     BIN_CUDA_OK(cudaMemsetAsync(g_dbg, 0, 3 * 4096 * sizeof(long long), s));
     p.dbg = g_dbg;
   }
-  auto kern = aligned ? rdb_tail_kernel<true> : rdb_tail_kernel<false>;
+  auto kern = streams ? rdb_tail_kernel<true> : rdb_tail_kernel<false>;
   static bool attr_done = false;
   if (!attr_done) {
     BIN_CUDA_OK(cudaFuncSetAttribute(rdb_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem));

@@ -1,4 +1,4 @@
-"""A/B inside one process (eager launches): unfused RDB tail vs the fused kernel (aligned / shifted LFF operand).
+"""A/B inside one process (eager launches): unfused RDB tail vs the fused kernel (two tile streams / hand-off between the MMA warps).
 Alternates the configurations so that clock / power drift hits all of them equally.  usage: ab_tail.py [rounds]"""
 import os
 import statistics
@@ -16,8 +16,8 @@ net = rdn.bin_stage4_lstm()
 net.load_state_dict(O.synth_state_dict(0), strict=True)
 net = net.cuda().eval()
 fr = [f.cuda() for f in O.synth_frames(6, 1, 720, 1280, seed=1234, smooth=True)]
-CFG = {"unfused": {"BIN_B200_FUSE_LFF": "0"}, "fused/aligned": {"BIN_B200_FUSE_LFF": "1", "BIN_B200_TAIL_ALIGNED": "1"},
-       "fused/shifted": {"BIN_B200_FUSE_LFF": "1", "BIN_B200_TAIL_ALIGNED": "0"}}
+CFG = {"unfused": {"BIN_B200_FUSE_LFF": "0"}, "fused/streams": {"BIN_B200_FUSE_LFF": "1", "BIN_B200_TAIL_STREAMS": "1"},
+       "fused/handoff": {"BIN_B200_FUSE_LFF": "1", "BIN_B200_TAIL_STREAMS": "0"}}
 times = {k: [] for k in CFG}
 ref = None
 with torch.no_grad():

@@ -22,9 +22,11 @@ a = list(buf)
 def role(r, n): return [[a[r * 4096 + i * 4 + j] for j in range(4)] for i in range(n)]
 prod, mma, epa = role(0, 400), role(1, 240), role(2, 67)
 t0 = min(v for v in (prod[0][0], mma[0][0], epa[0][0]) if v)
-print("variant aligned =", os.environ.get("BIN_B200_TAIL_ALIGNED", "1"))
+print("variant streams =", os.environ.get("BIN_B200_TAIL_STREAMS", "1"))
 for i in range(36, 48):
     m = mma[i]
+    if m[2] == 0:
+        m[2] = m[1]                      # two-stream variant: no turn wait
     print("mma item", i, "(c=%d)" % (2 * (i % 3)), [v - t0 for v in m], "wait_data=%d wait_turn=%d issue=%d gap=%d" % (m[1] - m[0], m[2] - m[1], m[3] - m[2], mma[i + 1][0] - m[3]))
 for i in range(120, 132):
     print("prod stage", i, prod[i][0] - t0, "wait_empty=%d" % (prod[i][1] - prod[i][0]))
