@@ -207,7 +207,7 @@ def dominant_kernel_roofline(torch, ops, pk, ncalls, h, w):
                             f"{tail_bytes:.4g} (576 B/position: 192 input channels in, 96 out; the residual re-read hits L2)",
             "tflops": tail_flops / (tail_ms * 1e-3) / 1e12, "ms_per_launch": tail_ms,
             "note": "bound by neither roof: 150 KB of resident weights leave a 4 x 12 KB activation ring, the kernel runs "
-                    "at the ring's latency (DESIGN.md 5d)"}
+                    "at the latency of that ring (DESIGN.md 4c)"}
     return {"bound": "tensor", "kernel": "conv_igemm_kernel<32,3,P8,SX> (RDB 3x3 convs 0..2, 3 shapes)", "achieved": ach,
             "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "traffic": 1.0537e9 if (ncalls, h, w) == (5, 360, 640) else None,
