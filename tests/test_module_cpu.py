@@ -80,3 +80,24 @@ def test_workspace_queries_are_pure():
     assert L.bin_backbone_packed_bytes(2) > 5_000_000 and L.bin_backbone_packed_bytes(4) == 0
     a = L.bin_window_workspace_bytes(1, 64, 64)
     assert 0 < a < L.bin_window_workspace_bytes(1, 128, 128)
+
+
+def test_training_side_modules_refuse_cpu_tensors():
+    """bin_b200.optim / bin_b200.dataprep have no CPU path: they must say so instead of computing something."""
+    import torch
+    from bin_b200 import BinB200Error
+    from bin_b200.dataprep import blur_average, window_count
+    from bin_b200.optim import Adam
+    p = torch.nn.Parameter(torch.ones(4))
+    p.grad = torch.ones(4)
+    opt = Adam([p], lr=1e-3, betas=(0.9, 0.99), weight_decay=1e-4)
+    assert opt.param_groups[0]["betas"] == (0.9, 0.99) and opt.param_groups[0]["weight_decay"] == 1e-4
+    with pytest.raises(BinB200Error):
+        opt.step()
+    assert torch.all(p == 1)
+    with pytest.raises(ValueError):
+        Adam([p], lr=-1.0)
+    with pytest.raises(BinB200Error):
+        blur_average(torch.zeros((40, 4, 4, 3), dtype=torch.uint8))
+    # create_dataset_blur_N_frames_average.py:104  window_total_num = floor(n_length / 8) - 2
+    assert [window_count(n) for n in (24, 40, 47, 48, 240)] == [1, 3, 3, 4, 28]
