@@ -82,7 +82,9 @@ def test_rdb_shapes_vs_oracle(net, sd, B, H, W):
     assert torch.isfinite(y).all()
     assert (y - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
 
-@pytest.mark.parametrize("B,H,W,sub", [(2, 9, 37, (0, 0, 0, 0)), (3, 16, 64, (1, 2, 4, 7)), (1, 4, 30, (0, 1, 0, 4)), (1, 70, 45, (0, 0, 3, 0))])
+@pytest.mark.parametrize("B,H,W,sub", [(2, 9, 37, (0, 0, 0, 0)), (3, 16, 64, (1, 2, 4, 7)), (1, 4, 30, (0, 1, 0, 4)), (1, 70, 45, (0, 0, 3, 0)),
+                                       (4, 120, 200, (0, 0, 0, 0)),      # 840 tiles: 5-6 per CTA, both tile streams, 3 LFF accumulators
+                                       (1, 148, 90, (0, 0, 0, 0))])      # 111 tiles... one per CTA on most, none on the rest
 def test_rdb_tail_bit_identical_to_layerwise(B, H, W, sub):
     """bin_rdb_tail_fwd == conv3 (x-stacked kernel) followed by the LFF kernel, bit for bit (same accumulation order),
     on full tensors and on batch / row sub-ranges (rows outside the range must stay untouched)."""
