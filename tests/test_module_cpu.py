@@ -101,3 +101,33 @@ def test_training_side_modules_refuse_cpu_tensors():
         blur_average(torch.zeros((40, 4, 4, 3), dtype=torch.uint8))
     # create_dataset_blur_N_frames_average.py:104  window_total_num = floor(n_length / 8) - 2
     assert [window_count(n) for n in (24, 40, 47, 48, 240)] == [1, 3, 3, 4, 28]
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every ABI struct as gcc sees include/bin_b200.h == the ctypes mirror in bin_b200/_lib.py
+    (and the 5 x int64 rows bin_b200.optim uploads == bin_adam_tensor_t)."""
+    import ctypes as C
+    import subprocess
+    from bin_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probes = {"bin_act_t": (_lib.Act, ["ptr", "B", "planes", "H", "W"]),
+              "bin_frames_t": (_lib.Frames, ["frame", "out", "ncalls", "nframes", "Bc"]),
+              "bin_conv_args_t": (_lib.ConvArgs, [f[0] for f in _lib.ConvArgs._fields_]),
+              "bin_net_t": (_lib.Net, ["blob", "lstm_w", "lstm_b"])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "bin_b200.h"', 'int main(void) {']
+    for cname, (_, fields) in probes.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ['  printf("bin_adam_tensor_t %zu\\n", sizeof(bin_adam_tensor_t));',
+              '  printf("bin_adam_tensor_t.n %zu\\n", offsetof(bin_adam_tensor_t, n));', '  return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, (ct, fields) in probes.items():
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for f in fields:
+            assert int(got[f"{cname}.{f}"]) == getattr(ct, f).offset, f"{cname}.{f}"
+    assert int(got["bin_adam_tensor_t"]) == 5 * 8 and int(got["bin_adam_tensor_t.n"]) == 4 * 8
