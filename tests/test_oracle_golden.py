@@ -140,3 +140,17 @@ def test_blur_average(golden_dir, ws):
     assert list(d[f"ws{ws}_mid"]) == [16, 24, 32, 40]
     out = O.blur_average(d["frames"], window_size=ws)
     assert out.dtype == np.uint8 and np.array_equal(out, d[f"ws{ws}_out"])
+
+
+@pytest.mark.parametrize("ws", [1, 7, 8, 11, 255])
+def test_blur_average_float_formula_equals_integer_floor(ws):
+    """The script's float32 sum / float32 count / astype(uint8) (:117-130) equals integer floor division for every
+    reachable sum, so the CUDA kernel (integer accumulation + one IEEE division) and the oracle agree for any input;
+    even window sizes average 2*int((ws-1)/2)+1 frames (:101, :129)."""
+    n = 2 * int((ws - 1) / 2) + 1
+    sums = np.arange(0, 255 * n + 1, dtype=np.int64)
+    got = (sums.astype(np.float32) / np.float32(n)).astype("uint8")
+    assert np.array_equal(got, (sums // n).astype(np.uint8))
+    frames = np.random.default_rng(ws).integers(0, 256, size=(2 * (n // 2) + 1, 3, 5), dtype=np.uint8)
+    out = O.blur_average(frames, window_size=ws, first_mid=n // 2, stride=1, nwin=1)
+    assert np.array_equal(out[0], (frames.astype(np.int64).sum(0) // n).astype(np.uint8))
