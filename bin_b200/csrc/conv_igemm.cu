@@ -649,11 +649,8 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
     p.dbg = g_dbg;
   }
   auto kern = conv_igemm_kernel<NT, KS, EPI, SX, X3>;
-  static bool attr_done = false;   // per instantiation; idempotent, so a benign race at worst
-  if (!attr_done) {
-    BIN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> smem_opted{0};   // per instantiation, per device
+  BIN_TRY(ensure_dynamic_smem(kern, kSmemMax, smem_opted));
   int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
   if (grid < 1) return BIN_OK;
   kern<<<grid, kThreads, smem_bytes, s>>>(p);

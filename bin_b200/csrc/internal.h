@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <string>
 
 #include "../../include/bin_b200.h"
@@ -23,6 +24,21 @@ int fail(int code, const std::string& msg);
     int _r = (expr);             \
     if (_r != BIN_OK) return _r; \
   } while (0)
+
+// cudaFuncSetAttribute acts on the CURRENT device's context: a process that drives several GPUs (nn.DataParallel
+// replicas, bin_model.py:40-42) must opt every kernel into its dynamic shared-memory size once per device.
+// `mask` is one static per kernel (instantiation); bit d = done on device d.
+template <typename Kernel>
+inline int ensure_dynamic_smem(Kernel kern, int bytes, std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  BIN_CUDA_OK(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(mask.load(std::memory_order_acquire) & bit)) {
+    BIN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));   // idempotent
+    mask.fetch_or(bit, std::memory_order_release);
+  }
+  return BIN_OK;
+}
 
 // ------------------------------------------------------------------ tile geometry of the conv kernel
 constexpr int kTWH = 32;   // smem row pitch of an activation tile, in pixels (= 4 UMMA row groups)

@@ -479,12 +479,8 @@ int launch_rdb_tail(const bin_act_t& x, int x_plane0, const bin_act_t& g, int g_
     p.dbg = g_dbg;
   }
   auto kern = streams ? rdb_tail_kernel<true> : rdb_tail_kernel<false>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    BIN_CUDA_OK(cudaFuncSetAttribute(rdb_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem));
-    BIN_CUDA_OK(cudaFuncSetAttribute(rdb_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem));
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> opted_streams{0}, opted_handoff{0};   // per device
+  BIN_TRY(ensure_dynamic_smem(kern, kRtSmem, streams ? opted_streams : opted_handoff));
   static int sms = []() {
     int dev = 0, v = 0;
     cudaGetDevice(&dev);

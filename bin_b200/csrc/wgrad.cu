@@ -223,11 +223,8 @@ int launch_wgrad_impl(const bin_act_t& x0, int x0_plane0, int x0_planes, const b
   if (S < 1) return fail(BIN_ERR_UNSUPPORTED, "wgrad: tile does not fit in shared memory");
   p.nstages = S;
   const int smem_bytes = 1024 + S * (x_bytes + y_bytes);
-  static bool attr_done = false;
-  if (!attr_done) {
-    BIN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> smem_opted{0};   // per device
+  BIN_TRY(ensure_dynamic_smem(wgrad_kernel, kSmemMax, smem_opted));
   const int kk = p.sx ? 3 : ks * ks;                  // SX: one accumulator per ky
   const int taps_per_group = 512 / n < kk ? 512 / n : kk;
   const int ci_planes = x0_planes + x1_planes;
