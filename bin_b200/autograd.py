@@ -23,8 +23,8 @@ def _stream() -> int:
 
 
 def _packed_t(model) -> torch.Tensor:
-    ps = list(model.parameters())
-    key = tuple((p.data_ptr(), p._version) for p in ps)
+    ps = model._conv_params()
+    key = (ps[0].device.index,) + tuple((p.data_ptr(), p._version) for p in ps)
     cached = model.__dict__.get("_packed_t")
     if cached is None or cached[0] != key:
         dev = ps[0].device
@@ -79,7 +79,7 @@ class BackboneStageFn(torch.autograd.Function):
                                          scale.data_ptr(), _stream()))
         ctx.save = None
         pgrads, off = [], 0
-        for p in model.parameters():
+        for p in model._conv_params():
             pgrads.append(gparams[off:off + p.numel()].view_as(p))
             off += p.numel()
         flat = [g for call in dframes for g in call]
@@ -88,7 +88,9 @@ class BackboneStageFn(torch.autograd.Function):
 
 def backbone_stage(model, calls: Sequence[Sequence[torch.Tensor]]) -> List[torch.Tensor]:
     flat = [t for c in calls for t in c]
-    return list(BackboneStageFn.apply(model, len(calls), *flat, *model.parameters()))
+    # the weights are passed as the module's ATTRIBUTES (replica-safe, see _Backbone._conv_params): in an nn.DataParallel
+    # replica they are Broadcast outputs whose gradients autograd reduces onto the master parameters
+    return list(BackboneStageFn.apply(model, len(calls), *flat, *model._conv_params()))
 
 
 def backbone_apply(module, frames):

@@ -17,6 +17,41 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 
+static Options read_options() {
+  Options o;
+  auto env = [](const char* k) { const char* e = getenv(k); return (e && *e) ? e : nullptr; };
+  const char* e;
+  o.debug = (e = env("BIN_B200_DEBUG")) ? atoi(e) : 0;
+  o.fuse_lff = !((e = env("BIN_B200_FUSE_LFF")) && *e == '0');
+  o.tail_streams = !((e = env("BIN_B200_TAIL_STREAMS")) && *e == '0');
+  o.pair = !((e = env("BIN_B200_PAIR")) && *e == '0');
+  o.band_budget = (e = env("BIN_B200_BAND_BUDGET_KB")) ? (size_t)atoll(e) << 10 : (~(size_t)0 >> 1);
+  return o;
+}
+const Options& options() {
+#ifdef BIN_B200_TOOLS
+  static thread_local Options o;
+  o = read_options();
+  return o;
+#else
+  static const Options o = read_options();
+  return o;
+#endif
+}
+
+int num_sms() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int v = cache[dev & 63].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    cache[dev & 63].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 int launch_nchw_to_p8(const float* x, int C, const bin_act_t& dst, int plane0, cudaStream_t s);
 int launch_p8_to_nchw(const bin_act_t& src, int plane0, int C, float* y, cudaStream_t s);
 int launch_pack_frames(const bin_frames_t& fr, int H, int W, const bin_act_t& dst, cudaStream_t s, int x3 = 0);
@@ -25,7 +60,6 @@ int launch_pack_weight(const float* w, int cout, int cin, int ks, int cout_pad, 
 int launch_pack_bias(const float* b, int cout, int cout_pad, float* dst, cudaStream_t s);
 int launch_convlstm(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
                     float* h_out, float* c_out, int B, int H, int W, cudaStream_t s);
-int run_mma_bench(int n, int iters, int mode, float* cycles_host);
 int launch_pixel_loss_fwd(const float* const* a, const float* const* b, int npairs, size_t n, int kind, float eps,
                           float* pair_loss, cudaStream_t s);
 int launch_pixel_loss_bwd(const float* const* a, const float* const* b, float* const* da, float* const* db, int npairs,
@@ -146,12 +180,10 @@ static bin_conv_args_t conv_args(const void* blob, const ConvSpec& c, int x3 = 0
 struct Band { int b0, nb, y0, y1; };   // batch items [b0,b0+nb), LFF output rows [y0,y1)
 constexpr size_t kBandBytesPerPx = 640;
 static size_t band_budget() {            // BIN_B200_BAND_BUDGET_KB overrides (tests force many bands)
-  const char* e = getenv("BIN_B200_BAND_BUDGET_KB");
-  if (e && *e) return (size_t)atoll(e) << 10;
   // Measured on B200 (720p, 5 batched calls): with 10 bands the 10x launch count costs more
   // (prologue + drain per launch, ~4 us each) than the L2 residency saves: 41.5 ms vs 31.8 ms per
-  // window.  Default = one band (off); the walker stays for the fused-RDB work of the next round.
-  return ~(size_t)0 >> 1;
+  // window.  Default = one band (off).
+  return options().band_budget;
 }
 
 static std::vector<Band> plan_bands(int Btot, int h, int w) {
@@ -168,7 +200,8 @@ static std::vector<Band> plan_bands(int Btot, int h, int w) {
   const int tx = (w + 29) / 30;
   const int T = (h + 7) / 8;                 // boundaries allowed at rows 8k-3, k = 1..T-1
   const int maxrows = (int)(px_max / w);
-  auto waves = [&](int rows) { int t = ((rows + 7) / 8) * tx; return (t + 147) / 148; };
+  const int sms = num_sms();
+  auto waves = [&](int rows) { int t = ((rows + 7) / 8) * tx; return (t + sms - 1) / sms; };
   // dp[k] = min waves to cover rows [0, 8k-3) with bands ending at k; last band ends at h.
   const int INF = 1 << 30;
   std::vector<int> dp(T + 1, INF), prev(T + 1, -1);
@@ -205,10 +238,7 @@ static std::vector<Band> plan_bands(int Btot, int h, int w) {
 // One RDB: 4 x (conv3x3+ReLU -> growth planes) + LFF 1x1 + residual (RDN.py:149-165).
 // The last conv and the LFF run as one kernel (rdb_tail.cu) in fp16 inference; training keeps them apart because the
 // backward needs the fourth growth map, and the split-fp16 mode has no fused variant.  BIN_B200_FUSE_LFF=0 disables it.
-static bool fuse_lff_enabled() {     // read per call (48 per window) so that tools can A/B it inside one process
-  const char* e = getenv("BIN_B200_FUSE_LFF");
-  return !(e && *e == '0');
-}
+static bool fuse_lff_enabled() { return options().fuse_lff; }
 static int run_rdb(const void* blob, const BackboneLayout& L, int i, const bin_act_t& xin, int x_plane0,
                    const bin_act_t& g, const bin_act_t& out, int out_plane0, const std::vector<Band>& bands,
                    cudaStream_t s, int g_plane0 = 0, int x3 = 0, bool keep_growth = false) {
@@ -317,7 +347,7 @@ int launch_bias_grad(const bin_act_t& dy, int plane0, int C, const float* scale,
 int launch_wgrad(const bin_act_t& x0, int x0_plane0, int x0_planes, const bin_act_t& x1, int x1_plane0, int x1_planes,
                  const bin_act_t& dy, int dy_plane0, int cout, int cin, int ks, const float* scale, float* dw,
                  float* partial_ws, cudaStream_t s);
-constexpr size_t kWgradPartialBytes = (size_t)148 * 128 * 512 * sizeof(float);   // per-CTA accumulator slabs
+static size_t wgrad_partial_bytes() { return (size_t)num_sms() * 128 * 512 * sizeof(float); }   // per-CTA accumulator slabs (grid = #SMs)
 
 struct TSpec {          // one data-gradient conv: output rows [row0,row0+nrows) of the forward conv's Cin axis
   int conv, row0, nrows, cout_pad_t, cin_pad_t, ks;
@@ -384,7 +414,7 @@ static GradWs grad_ws(int nframes, int Btot, int H, int W, void* base) {
   w.dg = carve(16, h, wd);
   w.dx0 = carve((int)align_up(12 * nframes, kKC) / 8, h, wd);
   w.wg_partial = base ? (float*)((uint8_t*)base + off) : nullptr;
-  off = align_up(off + kWgradPartialBytes, 256);
+  off = align_up(off + wgrad_partial_bytes(), 256);
   w.bytes = off;
   return w;
 }
@@ -541,7 +571,7 @@ int bin_pack_conv_weight_t(const float* w_oihw, int cout, int cin, int ksize, in
                            int cin_pad_t, void* packed, bin_stream_t s) {
   return launch_pack_weight_t(w_oihw, cout, cin, ksize, row0, nrows, cout_pad_t, cin_pad_t, packed, (cudaStream_t)s);
 }
-size_t bin_conv_wgrad_workspace_bytes(void) { return kWgradPartialBytes; }
+size_t bin_conv_wgrad_workspace_bytes(void) { return wgrad_partial_bytes(); }
 int bin_conv_wgrad(bin_act_t x0, int x0_plane0, int x0_planes, bin_act_t x1, int x1_plane0, int x1_planes, bin_act_t dy,
                    int dy_plane0, int cout, int cin, int ksize, const float* scale_dev, float* dw, void* workspace,
                    bin_stream_t s) {
@@ -771,15 +801,5 @@ int bin_blur_average_u8(const uint8_t* frames, int T, size_t frame_bytes, int wi
   if (!frames || !out) return fail(BIN_ERR_ARG, "blur_average: null argument");
   return launch_blur_average_u8(frames, T, frame_bytes, window_size, first_mid, stride, nwin, out, (cudaStream_t)s);
 }
-
-int bin_debug_timeline(long long* host, int n) {
-  if (!g_dbg) return fail(BIN_ERR_ARG, "no timeline recorded (set BIN_B200_DEBUG=8)");
-  if (n > 3 * 4096) n = 3 * 4096;
-  BIN_CUDA_OK(cudaDeviceSynchronize());
-  BIN_CUDA_OK(cudaMemcpy(host, g_dbg, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
-  return BIN_OK;
-}
-
-int bin_microbench_mma(int n, int iters, int mode, float* cycles_host) { return run_mma_bench(n, iters, mode, cycles_host); }
 
 }  // extern "C"

@@ -82,7 +82,9 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
 // perf-debug timeline (BIN_B200_DEBUG=8): block 0 records clock64 at role milestones.
 // layout: dbg[role*4096 + iter*4 + k], role 0 = producer A, 1 = MMA warp A, 2 = epilogue (warp 4).
 __device__ __forceinline__ void dbg_rec(const ConvParams& p, int role, uint32_t iter, int k) {
+#ifdef BIN_B200_TOOLS       // the product library carries no timeline hooks
   if ((p.debug & 8) && blockIdx.x == 0 && iter < 1024) p.dbg[role * 4096 + iter * 4 + k] = clock64();
+#endif
 }
 
 constexpr int kThreads = 384;   // 12 warps, see the role table below
@@ -580,16 +582,6 @@ int make_p8_tmap_box(CUtensorMap* m, const bin_act_t& t, int box_px, int box_row
   return BIN_OK;
 }
 
-static int num_sms() {
-  static int n = []() {
-    int dev = 0, v = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
-  return n;
-}
-
 template <int NT, int KS, int EPI, bool SX, bool X3>
 static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
   using C = ConvCfg<NT, KS, SX>;
@@ -642,12 +634,14 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
   p.store_planes = a.store_planes > 0 ? a.store_planes : a.cout_pad / 8;
   p.res = reinterpret_cast<const __half*>(a.res.ptr); p.res_planes = a.res.planes; p.res_plane0 = a.res_plane0;
   p.fr = a.fr;
-  { const char* e = getenv("BIN_B200_DEBUG"); p.debug = (e && *e) ? atoi(e) : 0; }   // perf experiments only
+  p.debug = options().debug;
+#ifdef BIN_B200_TOOLS
   if (p.debug & 8) {
     if (!g_dbg) { BIN_CUDA_OK(cudaMalloc(&g_dbg, 3 * 4096 * sizeof(long long))); }
     BIN_CUDA_OK(cudaMemsetAsync(g_dbg, 0, 3 * 4096 * sizeof(long long), s));
     p.dbg = g_dbg;
   }
+#endif
   auto kern = conv_igemm_kernel<NT, KS, EPI, SX, X3>;
   static std::atomic<unsigned long long> smem_opted{0};   // per instantiation, per device
   BIN_TRY(ensure_dynamic_smem(kern, kSmemMax, smem_opted));

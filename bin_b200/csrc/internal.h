@@ -40,6 +40,20 @@ inline int ensure_dynamic_smem(Kernel kern, int bytes, std::atomic<unsigned long
   return BIN_OK;
 }
 
+// ------------------------------------------------------------------ process options
+// Environment knobs of the library (documented in DESIGN.md).  The product build reads them ONCE per process (no
+// getenv on the launch path); the tools build (-DBIN_B200_TOOLS) re-reads them on every call so that a tool can A/B
+// configurations inside one process.
+struct Options {
+  int debug;                 // BIN_B200_DEBUG   bit 3: role timeline (tools build only), bit 4: synchronise after each conv launch
+  bool fuse_lff;             // BIN_B200_FUSE_LFF=0 runs conv3 and LFF as two launches instead of rdb_tail_kernel
+  bool tail_streams;         // BIN_B200_TAIL_STREAMS=0 selects the hand-off variant of rdb_tail_kernel
+  bool pair;                 // BIN_B200_PAIR=0 disables the CTA-pair (cta_group::2) kernels
+  size_t band_budget;        // BIN_B200_BAND_BUDGET_KB (L2 band walker; default: one band)
+};
+const Options& options();
+int num_sms();               // SM count of the current device (cached per device)
+
 // ------------------------------------------------------------------ tile geometry of the conv kernel
 constexpr int kTWH = 32;   // smem row pitch of an activation tile, in pixels (= 4 UMMA row groups)
 constexpr int kTH = 8;     // output rows per CTA tile

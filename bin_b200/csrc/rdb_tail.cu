@@ -67,7 +67,9 @@ struct alignas(64) RdbTailParams {
 // timeline layout (bin_debug_timeline): [role][iter][4]; role 0 = producer (k 0,1 per stage) and epilogue B (k 2,3 per tile),
 // role 1 = MMA warp 1 (per item it owns: before / after the data wait, after the turn wait, after the issue), role 2 = epilogue A
 __device__ __forceinline__ void rt_rec(const RdbTailParams& p, int role, uint32_t iter, int k) {
+#ifdef BIN_B200_TOOLS       // the product library carries no timeline hooks
   if ((p.debug & 8) && blockIdx.x == 0 && iter < 1024) p.dbg[role * 4096 + iter * 4 + k] = clock64();
+#endif
 }
 
 struct RtCtrl {
@@ -470,23 +472,19 @@ int launch_rdb_tail(const bin_act_t& x, int x_plane0, const bin_act_t& g, int g_
   p.ntiles = nb * p.tiles_x * p.tiles_y;
   p.out = reinterpret_cast<__half*>(out.ptr); p.out_planes = out.planes; p.out_plane0 = out_plane0;
   p.res = reinterpret_cast<const __half*>(x.ptr); p.res_planes = x.planes; p.res_plane0 = x_plane0;
-  const char* ea = getenv("BIN_B200_TAIL_STREAMS");
-  const bool streams = !(ea && *ea == '0');
-  { const char* e = getenv("BIN_B200_DEBUG"); p.debug = (e && *e) ? atoi(e) : 0; }   // perf experiments only
+  const bool streams = options().tail_streams;
+  p.debug = options().debug;
+#ifdef BIN_B200_TOOLS
   if (p.debug & 8) {
     if (!g_dbg) { BIN_CUDA_OK(cudaMalloc(&g_dbg, 3 * 4096 * sizeof(long long))); }
     BIN_CUDA_OK(cudaMemsetAsync(g_dbg, 0, 3 * 4096 * sizeof(long long), s));
     p.dbg = g_dbg;
   }
+#endif
   auto kern = streams ? rdb_tail_kernel<true> : rdb_tail_kernel<false>;
   static std::atomic<unsigned long long> opted_streams{0}, opted_handoff{0};   // per device
   BIN_TRY(ensure_dynamic_smem(kern, kRtSmem, streams ? opted_streams : opted_handoff));
-  static int sms = []() {
-    int dev = 0, v = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
+  const int sms = num_sms();
   const int grid = p.ntiles < sms ? p.ntiles : sms;
   kern<<<grid, 384, kRtSmem, s>>>(p);
   BIN_CUDA_OK(cudaGetLastError());

@@ -228,7 +228,8 @@ int launch_wgrad_impl(const bin_act_t& x0, int x0_plane0, int x0_planes, const b
   const int kk = p.sx ? 3 : ks * ks;                  // SX: one accumulator per ky
   const int taps_per_group = 512 / n < kk ? 512 / n : kk;
   const int ci_planes = x0_planes + x1_planes;
-  int grid = p.ntiles < 148 ? p.ntiles : 148;
+  const int sms = num_sms();
+  int grid = p.ntiles < sms ? p.ntiles : sms;
   if (grid < 1) return BIN_OK;
   for (int cp = 0; cp < ci_planes; cp += 16) {
     for (int t0 = 0; t0 < kk; t0 += taps_per_group) {

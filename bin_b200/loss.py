@@ -6,7 +6,7 @@ the 17 terms).  One reduction launch and one gradient launch replace ~50 element
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -14,6 +14,16 @@ from ._lib import BinB200Error, check, lib
 
 KINDS = {"l1": 0, "l2": 1, "cb": 2}                   # bin_model.py:54-59
 CYCLE_PAIRS_6V2 = ((1, 7), (5, 9), (2, 8))            # bin_model.py:409-416
+CYCLE_PAIRS_4V5 = ((1, 5),)                           # bin_model.py:405-408
+
+
+def cycle_pairs_for(nframes: int, version: int) -> Tuple[Tuple[int, int], ...]:
+    """The cycle terms bin_model.get_loss appends for a (nframes, version) configuration (bin_model.py:405-416)."""
+    if nframes == 6 and version == 2:
+        return CYCLE_PAIRS_6V2
+    if nframes == 4 and version == 5:
+        return CYCLE_PAIRS_4V5
+    return ()
 
 
 def _stream() -> int:
@@ -58,7 +68,19 @@ class PixelLossFn(torch.autograd.Function):
 
 
 def pixel_loss(outs: Sequence[torch.Tensor], gts: Sequence[torch.Tensor], kind: str = "l1", eps: float = 1e-6,
-               cycle_pairs: Sequence[Tuple[int, int]] = CYCLE_PAIRS_6V2) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+               cycle_pairs: Optional[Sequence[Tuple[int, int]]] = None, nframes: Optional[int] = None,
+               version: int = 2) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    """`cycle_pairs` defaults to what get_loss uses for (nframes, version); nframes defaults to 6 for the shipped
+    14-output graph and must be given (or cycle_pairs passed) for any other output count."""
+    if cycle_pairs is None:
+        if nframes is None:
+            if len(outs) != 14:
+                raise BinB200Error("pixel_loss: pass nframes/version (bin_model.get_info) or cycle_pairs when the graph "
+                                   "does not have the shipped 14 outputs")
+            nframes = 6
+        cycle_pairs = cycle_pairs_for(nframes, version)
+    if any(max(i, j) >= len(outs) for i, j in cycle_pairs):
+        raise BinB200Error("pixel_loss: cycle pair index outside the output list")
     if kind not in KINDS:
         raise BinB200Error(f"unknown pixel criterion {kind!r} (bin_model.py:54-61 knows l1, l2, cb)")
     if len(outs) != len(gts):

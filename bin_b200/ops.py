@@ -57,7 +57,21 @@ def p8_to_nchw(src: torch.Tensor, C_: int, plane0: int = 0) -> torch.Tensor:
     return y
 
 
+def _req_contig(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    """Like _req but never copies: the caller stores a raw pointer, and a temporary `.contiguous()` copy would be freed
+    (and its block handed to the next allocation on this stream) before the kernel that reads it is launched."""
+    if not t.is_cuda:
+        raise _lib.BinB200Error(f"{name}: expected a CUDA tensor (bin_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.BinB200Error(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.BinB200Error(f"{name}: expected a contiguous tensor (call .contiguous() and keep the result alive)")
+    return t
+
+
 def make_frames(calls: Sequence[Sequence[torch.Tensor]], outs: Sequence[Optional[torch.Tensor]]) -> Frames:
+    """Pointer table of a batched backbone launch.  Holds raw pointers: every tensor must be contiguous and must stay
+    alive until the launch that consumes the table has been enqueued."""
     fr = Frames()
     fr.ncalls = len(calls)
     fr.nframes = len(calls[0])
@@ -65,7 +79,7 @@ def make_frames(calls: Sequence[Sequence[torch.Tensor]], outs: Sequence[Optional
     for k, frames in enumerate(calls):
         assert len(frames) == fr.nframes
         for f, t in enumerate(frames):
-            fr.frame[k][f] = _req(t, torch.float32, "frame").data_ptr()
+            fr.frame[k][f] = _req_contig(t, torch.float32, "frame").data_ptr()
         fr.out[k] = _ptr(outs[k])
     return fr
 
@@ -145,9 +159,3 @@ def convlstm_fwd(x, w, b, state=None):
     check(lib().bin_convlstm_fwd(x.data_ptr(), _ptr(cp), _ptr(hp), _req(w, torch.float32, "w").data_ptr(),
                                  _req(b, torch.float32, "b").data_ptr(), h.data_ptr(), c.data_ptr(), B, H, W, _stream()))
     return h, c
-
-
-def microbench_mma(n: int, iters: int = 4096, mode: int = 0) -> float:
-    v = C.c_float(0)
-    check(lib().bin_microbench_mma(n, iters, mode, C.byref(v)))
-    return v.value

@@ -32,6 +32,8 @@ class _Table:
         dev = params[0].device
         n = len(params)
         self.key = tuple(p.data_ptr() for p in params) + tuple(m.data_ptr() for m in ms)
+        self.pkey = self.key[:n]
+        self.params = list(params)
         self.host = torch.zeros((n, 5), dtype=torch.int64).pin_memory()
         h = self.host.numpy()
         h[:, 0] = [p.data_ptr() for p in params]
@@ -84,6 +86,10 @@ class Adam(torch.optim.Optimizer):
             check(lib().bin_adam_step(tab.dev.data_ptr(), tab.prefix.data_ptr(), tab.n, tab.nchunks,
                                       float(group["lr"]), beta1, beta2, group["eps"], group["weight_decay"],
                                       1.0 - beta1 ** step, 1.0 - beta2 ** step, grad_scale, _stream()))
+        # The kernel writes the parameters through raw device pointers, which autograd's version counter does not see.
+        # Every weight cache of the package (packed fp16 blobs, transposed blobs, the CUDA-graph key) is keyed on
+        # (data_ptr, _version): without this bump the network would keep running on the weights packed BEFORE the step.
+        torch._C._increment_version(tab.params)
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -98,7 +104,9 @@ class Adam(torch.optim.Optimizer):
             # steady state: same parameter objects as last step, every one with a dense contiguous gradient, one shared
             # step counter -> no per-tensor Python work beyond reading 540 gradient pointers
             if (tab is not None and tab.shared_step is not None and tab.ids == [id(p) for p in params]
-                    and all(g is not None and g.is_contiguous() for g in grads)):
+                    and tab.pkey == tuple(p.data_ptr() for p in params)          # p.data re-homed (.to(), p.data = ...)?
+                    and all(g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.device == tab.dev.device
+                            and not g.is_sparse for g in grads)):
                 self._launch(tab, grads, group, float(tab.step_value) + 1.0, grad_scale)
                 tab.shared_step += 1
                 tab.step_value += 1

@@ -154,15 +154,29 @@ class _Backbone(nn.Module):
         self._packed_key = None
 
     # -- packed weights (cached per parameter version / device) ---------------------------------
-    def _conv_params(self) -> List[nn.Parameter]:
-        ps = list(self.parameters())
-        assert len(ps) == 2 * _lib.BIN_BACKBONE_NCONV
+    def _conv_modules(self) -> List[nn.Conv2d]:
+        """The 66 convs in nn.Module registration order (= the order of bin_backbone_pack's pointer tables)."""
+        ms = [self.SFENet1, self.SFENet2]
+        for blk in self.RDBs:
+            ms += [rc.conv[0] for rc in blk.convs] + [blk.LFF]
+        ms += [self.GFF[0], self.GFF[1], self.UPNet[0], self.UPNet[2]]
+        return ms
+
+    def _conv_params(self) -> List[torch.Tensor]:
+        """[w0, b0, w1, b1, ...] read from the conv modules' attributes, NOT from self.parameters(): an
+        nn.DataParallel replica (bin_model.py:42) has empty _parameters and carries its broadcast weight copies as
+        plain tensor attributes (torch/nn/parallel/replicate.py), and those are the tensors a replica must run on."""
+        ps: List[torch.Tensor] = []
+        for m in self._conv_modules():
+            ps += [m.weight, m.bias]
+        if len(ps) != 2 * _lib.BIN_BACKBONE_NCONV:
+            raise BinB200Error("backbone does not hold the 66 convs of RDN.py:187-208")
         return ps
 
     def packed_blob(self, prec: int = 0) -> torch.Tensor:
         """Packed weights for BIN_PREC_F16 (0) or BIN_PREC_F32X3 (1), cached per parameter version."""
         ps = self._conv_params()
-        key = (prec,) + tuple((p.data_ptr(), p._version) for p in ps)
+        key = (prec, ps[0].device.index) + tuple((p.data_ptr(), p._version) for p in ps)
         if prec:
             cached = self.__dict__.get("_packed_x3")
             if cached is None or cached[0] != key:
@@ -253,15 +267,27 @@ def set_precision(net: nn.Module, precision: str) -> nn.Module:
     return net
 
 
+def _ws_key(dev: torch.device):
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return (idx, torch.cuda.current_stream(idx).cuda_stream)
+
+
 def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
-    """Grow-only scratch buffer per device (the C ABI never allocates)."""
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    """Grow-only scratch buffer per (device, stream) -- the C ABI never allocates, and two streams (or the worker
+    threads of nn.DataParallel, one per replica device, bin_model.py:42) must never share scratch memory: launches on
+    different streams are not ordered against each other.  Same-stream callers reuse one buffer (stream order)."""
+    key = _ws_key(dev)
     cur = _WS.get(key)
     if cur is None or cur.numel() < nbytes:
         _WS[key] = None
         cur = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         _WS[key] = cur
     return cur
+
+
+def release_workspaces() -> None:
+    """Drop every cached scratch buffer (they are re-created on demand)."""
+    _WS.clear()
 
 
 # --------------------------------------------------------------------------------------------
@@ -339,6 +365,17 @@ class RDN_residual_interp_5_input_ConvLSTM_L(nn.Module):
         self.prev_state = None
         self.hidden_state = None
 
+    def _all_tensors(self) -> List[torch.Tensor]:
+        """Every weight the window reads (4 unique backbones + 6 ConvLSTM cells), replica-safe (see _conv_params)."""
+        pyr = self.model
+        ts: List[torch.Tensor] = []
+        for m in (pyr.model1_1, pyr.model2_1, pyr.model3_1, pyr.model4_1):
+            ts += m._conv_params()
+        for n in _LSTM_NAMES:
+            g = getattr(self, n).Gates
+            ts += [g.weight, g.bias]
+        return ts
+
     def _net(self, prec: int = 0) -> Net:
         net = Net()
         pyr = self.model
@@ -355,7 +392,7 @@ class RDN_residual_interp_5_input_ConvLSTM_L(nn.Module):
         backbone calls of its 20 and the 6 live ConvLSTM calls of its 12."""
         frames = [B1, B3, B5, B7, B9, B11]
         if torch.is_grad_enabled() and (any(f.requires_grad for f in frames) or
-                                        any(p.requires_grad for p in self.parameters())):
+                                        any(p.requires_grad for p in self._all_tensors())):
             from .autograd import window_apply
             return window_apply(self, frames)
         frames = [f.contiguous() for f in frames]
@@ -364,7 +401,7 @@ class RDN_residual_interp_5_input_ConvLSTM_L(nn.Module):
         if _graphs_enabled() and not getattr(self, "_is_replica", False) and not torch.cuda.is_current_stream_capturing():
             return self._forward_graphed(frames, B, H, W, dev)
         with torch.cuda.device(dev):
-            return tuple(self._launch_window(frames, B, H, W, dev))
+            return tuple(self._launch_window(frames, B, H, W, dev)[0])
 
     def _launch_window(self, frames, B, H, W, dev):
         outs = [torch.empty_like(frames[0]) for _ in range(14)]
@@ -374,13 +411,13 @@ class RDN_residual_interp_5_input_ConvLSTM_L(nn.Module):
         fp = (C.c_void_p * 6)(*[f.data_ptr() for f in frames])
         op = (C.c_void_p * 14)(*[o.data_ptr() for o in outs])
         check(lib().bin_window_fwd_p(C.byref(net), fp, op, B, H, W, ws.data_ptr(), ws.numel(), prec, _stream()))
-        return outs
+        return outs, ws
 
     def _forward_graphed(self, frames, B, H, W, dev):
         """The ~340 kernel launches of a window are captured once per (shape, weight version) into a
         CUDA graph and replayed: removes ~10 % of host launch overhead at 720p.  Inputs are copied
         into the graph's static buffers, outputs are returned as fresh tensors."""
-        key = (dev.index, B, H, W, _prec_of(self), tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        key = (dev.index, B, H, W, _prec_of(self), tuple((p.data_ptr(), p._version) for p in self._all_tensors()))
         ent = self.__dict__.get("_graph_entry")
         with torch.cuda.device(dev):
             if ent is None or ent["key"] != key:
@@ -390,14 +427,15 @@ class RDN_residual_interp_5_input_ConvLSTM_L(nn.Module):
                     d.copy_(f)
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):                       # warm-up: packs weights, sizes the workspace
+                with torch.cuda.stream(side):                       # warm-up: packs weights, opts kernels into their smem
                     self._launch_window(static_in, B, H, W, dev)
+                    _WS.pop(_ws_key(dev), None)                     # the side stream's scratch buffer is not needed again
                 torch.cuda.current_stream().wait_stream(side)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    static_out = self._launch_window(static_in, B, H, W, dev)
-                ent = {"key": key, "graph": graph, "in": static_in, "out": static_out,
-                       "ws": _workspace(dev, 0)}                    # keeps the captured workspace alive
+                    static_out, ws = self._launch_window(static_in, B, H, W, dev)
+                    _WS.pop(_ws_key(dev), None)                     # owned by this entry (graph-private memory pool)
+                ent = {"key": key, "graph": graph, "in": static_in, "out": static_out, "ws": ws}
                 self.__dict__["_graph_entry"] = ent
             else:
                 for d, f in zip(ent["in"], frames):
@@ -408,7 +446,7 @@ class RDN_residual_interp_5_input_ConvLSTM_L(nn.Module):
     def forward_pyramid3(self, B1, B3, B5, B7):
         """BASELINE config 2a: stages 1-3 on 4 frames -> [I2',I4',I6',I3',I5',I4'']."""
         if torch.is_grad_enabled() and (any(f.requires_grad for f in (B1, B3, B5, B7)) or
-                                        any(p.requires_grad for p in self.model.parameters())):
+                                        self.model.model1_1.SFENet1.weight.requires_grad):
             from .autograd import pyramid3_apply                      # BASELINE config 3a (training on the 4-frame graph)
             return pyramid3_apply(self, (B1, B3, B5, B7))
         frames = [f.contiguous() for f in (B1, B3, B5, B7)]

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BIN_ABI_VERSION 1
+#define BIN_ABI_VERSION 2
 #define BIN_MAX_CALLS 6   /* same-weight backbone calls batched along N */
 #define BIN_MAX_FRAMES 5  /* frames per backbone call (2, 3 or 5) */
 #define BIN_MAX_LOSS_PAIRS 20 /* (prediction, target) pairs of one fused loss call */
@@ -250,15 +250,6 @@ int bin_adam_step(const bin_adam_tensor_t* table_dev, const int* chunk_prefix_de
  * (script: window_size 11, first_mid 16, stride 8, nwin = floor(T/8) - 2). */
 int bin_blur_average_u8(const uint8_t* frames, int T, size_t frame_bytes, int window_size, int first_mid, int stride,
                         int nwin, uint8_t* out, bin_stream_t s);
-
-/* ---- measurement helpers ---------------------------------------------------------------- */
-/* Issue `iters` back-to-back tcgen05.mma (M=128, N=n, K=16, fp16) from one CTA per SM and
- * return cycles per MMA in *cycles_host (host pointer; synchronises). mode 0: A/B K-major
- * no-swizzle. */
-int bin_microbench_mma(int n, int iters, int mode, float* cycles_host);
-/* Perf tooling: with env BIN_B200_DEBUG=8 the conv kernel's block 0 records clock64 at role milestones
- * ([role 0 producer,1 MMA,2 epilogue][iter][k] as 3x1024x4 int64); copies the last launch's timeline. */
-int bin_debug_timeline(long long* host, int n);
 
 #ifdef __cplusplus
 }

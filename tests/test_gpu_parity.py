@@ -12,6 +12,7 @@ import torch
 from oracle import bin_oracle as O
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL_FP16 = 1e-3
 TOL_FP32 = 1e-5
 
@@ -159,15 +160,26 @@ def test_window_vs_oracle_and_psnr(net, sd, B, H, W):
         assert abs(p_ref - p_got) <= 0.01, (k, p_ref, p_got)
 
 
-def test_window_many_l2_bands(net, sd, monkeypatch):
-    """Force the RDB band walker (L2 blocking) to cut a small image into several overlapping bands."""
-    monkeypatch.setenv("BIN_B200_BAND_BUDGET_KB", "700")         # ~17 low-res rows of 64 px per band
-    fr = O.synth_frames(6, 1, 112, 128, seed=21, smooth=True)
-    ref = O.window_forward(fr, sd)
-    with torch.no_grad():
-        outs = net(*[f.cuda() for f in fr])
-    for k in range(14):
-        assert (outs[k].cpu() - ref[k]).abs().max().item() <= TOL_FP16, k
+def test_window_many_l2_bands(sd):
+    """Force the RDB band walker (L2 blocking) to cut a small image into several overlapping bands.  The library reads
+    its environment options once per process, so this runs in a child process."""
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from oracle import bin_oracle as O\n"
+        "from bin_b200 import rdn\n"
+        "sd = O.synth_state_dict(0)\n"
+        "net = rdn.bin_stage4_lstm(); net.load_state_dict(sd, strict=True); net = net.cuda().eval()\n"
+        "fr = O.synth_frames(6, 1, 112, 128, seed=21, smooth=True)\n"
+        "ref = O.window_forward(fr, sd)\n"
+        "with torch.no_grad(): outs = net(*[f.cuda() for f in fr])\n"
+        "print('WORST', max((o.cpu() - r).abs().max().item() for o, r in zip(outs, ref)))\n" % ROOT)
+    env = dict(os.environ, BIN_B200_BAND_BUDGET_KB="700")          # ~17 low-res rows of 64 px per band
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = float(r.stdout.strip().split("WORST")[-1])
+    assert worst <= TOL_FP16, worst
 
 
 def test_pyramid3_config2a(net, sd):

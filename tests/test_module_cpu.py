@@ -71,7 +71,10 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/bin_b200.h but not exported"
     assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
-    assert _lib.lib().bin_abi_version() == 1
+    assert _lib.lib().bin_abi_version() == _lib.ABI_VERSION == int(re.search(r"#define BIN_ABI_VERSION (\d+)", hdr).group(1))
+    # measurement tooling lives in libbin_b200_tools.so / csrc/tools_abi.h, never in the product library or its header
+    assert not any(n.startswith(("bin_tools_", "bin_microbench", "bin_debug")) for n in declared)
+    assert not hasattr(L, "bin_tools_microbench_mma") and not hasattr(L, "bin_microbench_mma")
 
 
 def test_workspace_queries_are_pure():
@@ -131,3 +134,29 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         for f in fields:
             assert int(got[f"{cname}.{f}"]) == getattr(ct, f).offset, f"{cname}.{f}"
     assert int(got["bin_adam_tensor_t"]) == 5 * 8 and int(got["bin_adam_tensor_t.n"]) == 4 * 8
+
+
+def test_weight_walk_matches_parameters_and_survives_replication(net):
+    """nn.DataParallel replicas (bin_model.py:42) have EMPTY _parameters and carry their weights as plain attributes
+    (torch/nn/parallel/replicate.py): the tensors handed to the C ABI must therefore be read from the conv modules, in
+    the registration order bin_backbone_pack expects."""
+    import torch
+    for bb in (net.model.model1_1, net.model.model2_1, net.model.model3_1, net.model.model4_1):
+        walked, regs = bb._conv_params(), list(bb.parameters())
+        assert len(walked) == 132 and all(a is b for a, b in zip(walked, regs))
+    allt = net._all_tensors()
+    assert len(allt) == 540 and {id(t) for t in allt} == {id(p) for p in net.parameters()}
+    # what replicate() does to one module tree, on CPU: copy every module, drop _parameters, set plain tensor attributes
+    mods = list(net.modules())
+    copies = {id(m): m._replicate_for_data_parallel() for m in mods}
+    for m in mods:
+        r = copies[id(m)]
+        for key, child in m._modules.items():
+            setattr(r, key, copies[id(child)])
+        for key, p in m._parameters.items():
+            setattr(r, key, p.detach() * 2.0)
+    rep = copies[id(net)]
+    assert len(list(rep.parameters())) == 0                       # the reason self.parameters() cannot be used
+    rw = rep._all_tensors()
+    assert len(rw) == 540 and all(torch.equal(a, b * 2.0) for a, b in zip(rw, allt))
+    assert rep.model.model1_3 is rep.model.model1_1               # aliases stay aliases inside a replica

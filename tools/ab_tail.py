@@ -1,3 +1,5 @@
+import os
+os.environ.setdefault("BIN_B200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bin_b200", "libbin_b200_tools.so"))  # tools build: options are re-read per call
 """A/B inside one process (eager launches): unfused RDB tail vs the fused kernel (two tile streams / hand-off between the MMA warps).
 Alternates the configurations so that clock / power drift hits all of them equally.  usage: ab_tail.py [rounds]"""
 import os

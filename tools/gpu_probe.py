@@ -1,3 +1,14 @@
+import os
+os.environ.setdefault("BIN_B200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bin_b200", "libbin_b200_tools.so"))  # tools build: timeline hooks + microbenchmarks
+
+
+def microbench_mma(n, iters=4096, mode=0):
+    import ctypes as C
+    from bin_b200 import _lib
+    v = C.c_float(0)
+    _lib.check(_lib.lib().bin_tools_microbench_mma(n, iters, mode, C.byref(v)))
+    return v.value
+
 """First-contact GPU probe: tcgen05 issue rates and per-instantiation conv parity.
 Each case runs in its own subprocess (a device trap must not take the others down).
 Usage: python tools/gpu_probe.py [case ...]
@@ -19,13 +30,13 @@ def case_mma():
         for lb in (0, 1):
             for n in (16, 32, 64, 96, 128, 256):
                 mode = 2 | (la << 4) | (lb << 6)
-                res[f"A{names[la]}_B{names[lb]}_N{n}"] = round(ops.microbench_mma(n, 16384, mode), 2)
+                res[f"A{names[la]}_B{names[lb]}_N{n}"] = round(microbench_mma(n, 16384, mode), 2)
     for la in (0, 1):
         mode = (la << 4) | (la << 6)
-        res[f"A{names[la]}_1acc_N32"] = round(ops.microbench_mma(32, 16384, mode | 1), 2)
-        res[f"A{names[la]}_shift_N32"] = round(ops.microbench_mma(32, 16384, mode | 2 | 0x100), 2)
-        res[f"A{names[la]}_M64_N32"] = round(ops.microbench_mma(32, 16384, mode | 2 | 0x200), 2)
-        res[f"A{names[la]}_M64_N128"] = round(ops.microbench_mma(128, 16384, mode | 2 | 0x200), 2)
+        res[f"A{names[la]}_1acc_N32"] = round(microbench_mma(32, 16384, mode | 1), 2)
+        res[f"A{names[la]}_shift_N32"] = round(microbench_mma(32, 16384, mode | 2 | 0x100), 2)
+        res[f"A{names[la]}_M64_N32"] = round(microbench_mma(32, 16384, mode | 2 | 0x200), 2)
+        res[f"A{names[la]}_M64_N128"] = round(microbench_mma(128, 16384, mode | 2 | 0x200), 2)
     print(json.dumps(res))
 
 
@@ -92,7 +103,7 @@ def case_mmapat():
     res = {}
     for vary in range(8):
         res[f"A{'var' if vary & 1 else 'fix'}_B{'var' if vary & 2 else 'fix'}_{'data' if vary & 4 else 'zero'}"] = round(
-            ops.microbench_mma(96, 200, 0x1000 | vary), 2)
+            microbench_mma(96, 200, 0x1000 | vary), 2)
     print(json.dumps(res))
 
 
@@ -131,9 +142,9 @@ def case_mma2():
     from bin_b200 import ops
     res = {}
     for n in (32, 64, 96, 128, 192, 256):
-        res[f"pair_M256_N{n}"] = round(ops.microbench_mma(n, 8192, 0x2000), 2)
+        res[f"pair_M256_N{n}"] = round(microbench_mma(n, 8192, 0x2000), 2)
     for n in (96, 128, 256):
-        res[f"single_M128_N{n}"] = round(ops.microbench_mma(n, 8192, 2), 2)
+        res[f"single_M128_N{n}"] = round(microbench_mma(n, 8192, 2), 2)
     print(json.dumps(res))
 
 

@@ -1,3 +1,5 @@
+import os
+os.environ.setdefault("BIN_B200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bin_b200", "libbin_b200_tools.so"))  # tools build: timeline hooks + microbenchmarks
 import ctypes as C, json, os, sys
 os.environ["BIN_B200_DEBUG"] = os.environ.get("BIN_B200_DEBUG", "8")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,7 +16,7 @@ for _ in range(3):
     ops.conv_fwd(x, wp, bp, 3, 32, **kw)
 torch.cuda.synchronize()
 buf = (C.c_longlong * (3 * 4096))()
-_lib.check(_lib.lib().bin_debug_timeline(buf, 3 * 4096))
+_lib.check(_lib.lib().bin_tools_debug_timeline(buf, 3 * 4096))
 a = list(buf)
 def role(r, n, k): return [[a[r * 4096 + i * 4 + j] for j in range(k)] for i in range(n)]
 nch = cin // 32

@@ -1,3 +1,5 @@
+import os
+os.environ.setdefault("BIN_B200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bin_b200", "libbin_b200_tools.so"))  # tools build: timeline hooks + microbenchmarks
 """In-kernel role timeline (BIN_B200_DEBUG=8) for an arbitrary layer: usage timeline2.py {final|up0|lff|gff0|sfe1|conv3}"""
 import ctypes as C, os, sys
 os.environ["BIN_B200_DEBUG"] = "8"
@@ -38,7 +40,7 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); run(); e1.record(); torch.cuda.synchronize()
 print(which, "kernel ms", e0.elapsed_time(e1))
 buf = (C.c_longlong * (3 * 4096))()
-_lib.check(_lib.lib().bin_debug_timeline(buf, 3 * 4096))
+_lib.check(_lib.lib().bin_tools_debug_timeline(buf, 3 * 4096))
 a = list(buf)
 def role(r, n, k): return [[a[r * 4096 + i * 4 + j] for j in range(k)] for i in range(n)]
 mma = role(1, 40, 3); prod = role(0, 40, 2); epi = role(2, 40, 3)

@@ -1,3 +1,5 @@
+import os
+os.environ.setdefault("BIN_B200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bin_b200", "libbin_b200_tools.so"))  # tools build: timeline hooks + microbenchmarks
 """In-kernel role timeline of the fused RDB tail (BIN_B200_DEBUG=8), 5 x 360 x 640.  usage: timeline_tail.py"""
 import ctypes as C, os, sys
 os.environ["BIN_B200_DEBUG"] = "8"
@@ -17,7 +19,7 @@ for _ in range(3):
     run()
 torch.cuda.synchronize()
 buf = (C.c_longlong * (3 * 4096))()
-_lib.check(_lib.lib().bin_debug_timeline(buf, 3 * 4096))
+_lib.check(_lib.lib().bin_tools_debug_timeline(buf, 3 * 4096))
 a = list(buf)
 def role(r, n): return [[a[r * 4096 + i * 4 + j] for j in range(4)] for i in range(n)]
 prod, mma, epa = role(0, 400), role(1, 240), role(2, 67)
