@@ -24,7 +24,7 @@ static Options read_options() {
   o.debug = (e = env("BIN_B200_DEBUG")) ? atoi(e) : 0;
   o.fuse_lff = !((e = env("BIN_B200_FUSE_LFF")) && *e == '0');
   o.tail_streams = !((e = env("BIN_B200_TAIL_STREAMS")) && *e == '0');
-  o.pair = !((e = env("BIN_B200_PAIR")) && *e == '0');
+  o.pair = (e = env("BIN_B200_PAIR")) && *e == '1';     // CTA-pair kernels: opt-in until verified on hardware
   o.band_budget = (e = env("BIN_B200_BAND_BUDGET_KB")) ? (size_t)atoll(e) << 10 : (~(size_t)0 >> 1);
   return o;
 }

@@ -443,6 +443,311 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
   }
 }
 
+// ====================================================================================================================
+// CTA-pair version (tcgen05.mma.cta_group::2): the same computation on a (2,1,1) cluster.
+//
+// Why: the single-CTA kernel keeps 150 KB of weights resident, which leaves a 4 x 12 KB activation ring -- 48 KB in
+// flight per SM cannot cover the loaded HBM latency (MMA warps wait 300-1200 cycles per 8-MMA item).
+// A CTA pair shares B: each CTA holds 48 of the 96 B rows of every slab (75 KB), runs its OWN 128-pixel tile (A) and
+// its own accumulators / epilogues, and ONE 256 x 96 x 16 MMA issued by the leader feeds both.  That frees room for a
+// 10 x 12 KB ring per CTA (120 KB in flight) and cuts the per-SM operand fetch from 7 KB to 5.5 KB per MMA.
+//
+// Barrier plan (r = cluster rank, leader = rank 0; only the leader's two MMA warps issue):
+//   full[slot]    leader's barrier, 1 arrival (leader's producer, expect_tx 2 x 12 KB); both producers' TMA loads credit it
+//                 (cp.async.bulk.tensor...cta_group::2 with the leader's barrier address from mapa)
+//   empty[slot], conv_full, lff_full, h_empty   one tcgen05.commit...multicast::cluster (mask 0b11) signals the barrier
+//                 at the same offset in BOTH CTAs -> producers and epilogues only ever wait on CTA-local barriers
+//   h_full, lff_empty   leader's barriers counting 256 arrivals: the 128 epilogue threads of each CTA
+//                 (mbarrier.arrive.release.cluster on the mapa'd address; the MMA warps wait with acquire.cluster)
+//   wready        leader's barrier, 1 arrival from the peer once ITS weight halves have landed
+// Tile pair q = cluster + j * nclusters; CTA r owns tile 2q + r (a cluster with an odd tile count runs a dummy last
+// tile in the peer: valid loads, stores suppressed).  Streams, accumulator rotation and the per-accumulator MMA order
+// are those of rdb_tail_kernel<true>, so the result is bit-identical to it and to the layer-by-layer kernels.
+constexpr int kRpHalf = kRtN / 2;                        // B rows per CTA
+constexpr int kRpSlab = kKPL * kRpHalf * 16;             // [4 planes][48 rows][16 B] = 3 072
+constexpr int kRpPlane = kRpHalf * 16;                   // 768
+constexpr int kRpWChunk = 4 * kRpSlab;                   // conv ky = 0,1,2 + LFF slab halves of a chunk
+constexpr int kRpWBytes = kRtChunks * kRpWChunk + kRpSlab;
+constexpr int kRpR = 5;                                  // ring slots per stream
+constexpr int kRpStages = 2 * kRpR;
+constexpr int kRpSmem = kRtCtrl + kRpWBytes + 2 * kRtHBytes + kRpStages * kRtABytes;
+static_assert(kRpSmem <= kSmemMax, "rdb_tail pair shared memory");
+static_assert(kRpWBytes % 1024 == 0, "operand alignment");
+
+struct RpCtrl {
+  uint64_t full[kRpStages], empty[kRpStages];
+  uint64_t wfull[kRtChunks + 1];
+  uint64_t wready;
+  uint64_t conv_full[2];
+  uint64_t lff_full[3], lff_empty[3];
+  uint64_t h_full[2], h_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(RpCtrl) <= 512, "ctrl block");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) rdb_tail_pair_kernel(const __grid_constant__ RdbTailParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  RpCtrl* ctrl = reinterpret_cast<RpCtrl*>(smem);
+  float* sb_conv = reinterpret_cast<float*>(smem + 512);           // 32 floats
+  float* sb_lff = sb_conv + 32;                                    // 96 floats
+  uint8_t* res_w = smem + kRtCtrl;
+  uint8_t* htile = res_w + kRpWBytes;
+  uint8_t* stage0 = htile + 2 * kRtHBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int npt = (p.ntiles + 1) >> 1;                             // tile pairs
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmap0);
+    tma_prefetch_desc(&p.tmap1);
+    for (int i = 0; i < kRpStages; ++i) { mbar_init(&ctrl->full[i], 1); mbar_init(&ctrl->empty[i], 1); }
+    for (int i = 0; i <= kRtChunks; ++i) mbar_init(&ctrl->wfull[i], 1);
+    mbar_init(&ctrl->wready, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctrl->conv_full[i], 1);
+      mbar_init(&ctrl->h_full[i], 256);        // epilogue-A threads of both CTAs (used in the leader)
+      mbar_init(&ctrl->h_empty[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&ctrl->lff_full[i], 1);
+      mbar_init(&ctrl->lff_empty[i], 256);     // epilogue-B threads of both CTAs (used in the leader)
+    }
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) sb_conv[threadIdx.x] = p.b_conv[threadIdx.x];
+  else if (threadIdx.x < 128) sb_lff[threadIdx.x - 32] = p.b_lff[threadIdx.x - 32];
+  if (warp == 2) {
+    tmem_alloc_pair(&ctrl->tmem_base, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                              // both CTAs' barriers are initialised
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+
+  // tile of this CTA in pair q (the peer of an odd tail re-runs the last tile with its stores suppressed)
+  auto tile_of = [&](int q, int& txi, int& tyi, int& b, bool& live) {
+    int t = 2 * q + (int)rank;
+    live = t < p.ntiles;
+    if (!live) t = p.ntiles - 1;
+    txi = t % p.tiles_x; t /= p.tiles_x;
+    tyi = t % p.tiles_y;
+    b = p.b0 + t / p.tiles_y;
+  };
+
+  if ((warp == 0 || warp == 2) && lane == 0) {
+    // ========================================================== TMA producers (both CTAs; stream Y = warp >> 1)
+    const uint32_t Y = warp >> 1;
+    if (Y == 0) {
+      // this CTA's half (rows 48r .. 48r+47) of every B slab: 768 contiguous bytes per 8-channel plane
+      for (int c = 0; c <= kRtChunks; ++c) {
+        const int nslab = c < kRtChunks ? 4 : 1;
+        mbar_expect_tx(&ctrl->wfull[c], nslab * kRpSlab);
+        for (int sl = 0; sl < nslab; ++sl) {
+          const uint8_t* src = (c < kRtChunks && sl < 3) ? p.w_conv + (size_t)(c * 3 + sl) * kRtSlab
+                                                         : p.w_lff + (size_t)c * kRtSlab;
+          uint8_t* dst = res_w + c * kRpWChunk + sl * kRpSlab;
+          for (int pl = 0; pl < kKPL; ++pl)
+            bulk_load_1d(dst + pl * kRpPlane, src + pl * (kRtN * 16) + rank * kRpPlane, kRpPlane, &ctrl->wfull[c]);
+        }
+      }
+    }
+    const uint32_t full0 = mapa_u32(smem_u32(&ctrl->full[0]), 0);  // the LEADER's full barriers
+    uint32_t k = 0;
+    for (int j = (int)Y; (int)(cluster + j * nclusters) < npt; j += 2) {
+      int txi, tyi, b; bool live;
+      tile_of((int)(cluster + j * nclusters), txi, tyi, b, live);
+      const int x0 = txi * kRtTW - 1, y0 = p.y0 + tyi * kRtTH - 1;
+      for (int c = 0; c < kRtChunks; ++c, ++k) {
+        const uint32_t slot = Y * kRpR + k % kRpR;
+        const uint32_t par = (k / kRpR) & 1;
+        mbar_wait(&ctrl->empty[slot], par ^ 1);
+        if (rank == 0) mbar_expect_tx(&ctrl->full[slot], 2 * kRtABytes);
+        const bool seg1 = c >= 3;
+        tma_load_4d_pair(stage0 + (size_t)slot * kRtABytes, seg1 ? (const void*)&p.tmap1 : (const void*)&p.tmap0,
+                         full0 + slot * 8, x0 * 8, y0, seg1 ? p.plane0_1 + (c - 3) * kKPL : p.plane0_0 + c * kKPL, b);
+      }
+    }
+  } else if (warp == 1 && rank == 1) {
+    // ========================================================== peer: tell the leader when this CTA's B halves have landed
+    for (int c = 0; c <= kRtChunks; ++c) mbar_wait(&ctrl->wfull[c], 0);
+    if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctrl->wready), 0));
+  } else if ((warp == 1 || warp == 3) && rank == 0) {
+    // ========================================================== MMA issuers (leader only; warp converged, one elected lane)
+    const uint32_t Y = warp >> 1;
+    constexpr uint32_t idesc = umma_idesc_f16(256, kRtN);
+    constexpr uint32_t D_HI = (128u >> 4) | (1u << 14);                // SBO = 128 B, descriptor version 1
+    constexpr uint32_t A_LBO = ((uint32_t)kRtAPlane >> 4) << 16;
+    constexpr uint32_t B_LBO = ((uint32_t)kRpPlane >> 4) << 16;
+    constexpr uint32_t H_LBO = ((uint32_t)kRtHPlane >> 4) << 16;
+    const uint32_t stage_lo = ((smem_u32(stage0) >> 4) & 0x3FFFu) | A_LBO;
+    const uint32_t w_lo = ((smem_u32(res_w) >> 4) & 0x3FFFu) | B_LBO;
+    uint32_t k = 0, n = 0;
+    for (int j = (int)Y; (int)(cluster + j * nclusters) < npt; j += 2, ++n) {
+      const uint32_t lb = (uint32_t)j % 3;
+      // conv[Y] is free in BOTH CTAs: this warp waited for the g3 tiles of its previous tile pair (256 arrivals), which
+      // the epilogue-A warps write after reading the accumulator.  The rotating LFF accumulator was released three
+      // tile pairs ago (256 arrivals as well).
+      mbar_wait_cluster(&ctrl->lff_empty[lb], (((uint32_t)j / 3) & 1) ^ 1);
+      const uint32_t d_conv = tmem_base + Y * kRtN;
+      const uint32_t d_lff = tmem_base + kRtLffCol0 + lb * kRtN;
+      for (int c = 0; c < kRtChunks; ++c, ++k) {
+        const uint32_t slot = Y * kRpR + k % kRpR;
+        mbar_wait(&ctrl->full[slot], (k / kRpR) & 1);
+        if (n == 0) {
+          mbar_wait(&ctrl->wfull[c], 0);
+          if (c == 0) mbar_wait_cluster(&ctrl->wready, 0);
+        }
+        tc_fence_after();
+        const uint32_t a_lo = stage_lo + slot * (kRtABytes >> 4);
+        const uint32_t b_lo = w_lo + c * (kRpWChunk >> 4);
+        const uint32_t first = (c == 0) ? 0u : 1u;
+        if (elect_one()) {
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {                               // conv: A shifted by ky rows, B = slab ky
+#pragma unroll
+            for (int jj = 0; jj < kKC / 16; ++jj) {
+              const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + jj * 2 * (kRtAPlane >> 4) + ky * kTWH);
+              const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + jj * 2 * kRpHalf + ky * (kRpSlab >> 4));
+              umma_f16_ss_pair(d_conv, ad, bd, idesc, (jj == 0 && ky == 0) ? first : 1u);
+            }
+            if (ky == 1) {                                               // LFF: centre row, x-unshifted start, B = slab 3
+#pragma unroll
+              for (int jj = 0; jj < kKC / 16; ++jj) {
+                const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + jj * 2 * (kRtAPlane >> 4) + kTWH);
+                const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + jj * 2 * kRpHalf + 3 * (kRpSlab >> 4));
+                umma_f16_ss_pair(d_lff, ad, bd, idesc, jj == 0 ? first : 1u);
+              }
+            }
+          }
+          umma_commit_pair(&ctrl->empty[slot]);                          // frees the slot in both CTAs
+          if (c == kRtChunks - 1) umma_commit_pair(&ctrl->conv_full[Y]);
+        }
+        __syncwarp();
+      }
+      // tail of this tile pair: LFF accumulator += g3 tile * Wl[6]
+      {
+        const uint32_t hb = Y;
+        const uint32_t a_lo = ((smem_u32(htile + hb * kRtHBytes) >> 4) & 0x3FFFu) | H_LBO;
+        const uint32_t b_lo = w_lo + kRtChunks * (kRpWChunk >> 4);
+        mbar_wait_cluster(&ctrl->h_full[hb], ((uint32_t)j >> 1) & 1);
+        if (n == 0) mbar_wait(&ctrl->wfull[kRtChunks], 0);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int jj = 0; jj < kKC / 16; ++jj) {
+            const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + jj * 2 * (kRtHPlane >> 4));
+            const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + jj * 2 * kRpHalf);
+            umma_f16_ss_pair(d_lff, ad, bd, idesc, 1u);
+          }
+          umma_commit_pair(&ctrl->lff_full[lb]);
+          umma_commit_pair(&ctrl->h_empty[hb]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ========================================================== epilogue A: conv accumulator -> g3 tile (smem), both CTAs
+    const int q = warp & 3;
+    const uint32_t hfull0 = mapa_u32(smem_u32(&ctrl->h_full[0]), 0);
+    for (int j = 0; (int)(cluster + j * nclusters) < npt; ++j) {
+      const uint32_t as = (uint32_t)j & 1, uph = ((uint32_t)j >> 1) & 1;
+      mbar_wait(&ctrl->conv_full[as], uph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kRtN;
+      uint32_t v[96];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) tmem_ld16(taddr + 16 * i, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * i]));
+      tmem_ld_wait();
+      tc_fence_before();
+      uint4 o[4];
+      uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float f[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[32 + i + e]), 1);
+          const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[64 + i + e]), 2);
+          f[e] = fmaxf(((__uint_as_float(v[i + e]) + b1) + b2) + sb_conv[i + e], 0.f);
+        }
+        ow[i >> 1] = rt_pack_h2(f[0], f[1]);
+      }
+      mbar_wait(&ctrl->h_empty[as], uph ^ 1);                          // tail of tile pair j-2 has consumed this buffer
+      uint8_t* h = htile + as * kRtHBytes + (q * 32 + lane + 1) * 16;
+      if (lane < 31) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) *reinterpret_cast<uint4*>(h + kk * kRtHPlane) = o[kk];
+      }
+      fence_proxy_async();                                             // generic-proxy stores -> visible to tcgen05.mma
+      mbar_arrive_cluster(hfull0 + as * 8);                            // the accumulator has been read, the g3 tile is written
+    }
+  } else if (warp >= 8) {
+    // ========================================================== epilogue B: LFF accumulator + bias + x -> x', both CTAs
+    const int q = warp & 3;
+    const uint32_t lffempty0 = mapa_u32(smem_u32(&ctrl->lff_empty[0]), 0);
+    for (int j = 0; (int)(cluster + j * nclusters) < npt; ++j) {
+      int txi, tyi, b; bool live;
+      tile_of((int)(cluster + j * nclusters), txi, tyi, b, live);
+      const int y = p.y0 + tyi * kRtTH + q, x = txi * kRtTW + lane;
+      const bool valid = live && (lane < kRtTW) && (y < p.y0 + p.ny) && (x < p.W);
+      const uint32_t lb = (uint32_t)j % 3;
+      uint4 rbuf[12];                                                  // residual x (RDN.py:165), fetched before the wait
+#pragma unroll
+      for (int kk = 0; kk < 12; ++kk) {
+        const size_t off = ((((size_t)b * p.res_planes + p.res_plane0 + kk) * p.H + y) * p.W + x) * 8;
+        rbuf[kk] = valid ? *reinterpret_cast<const uint4*>(p.res + off) : make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait(&ctrl->lff_full[lb], ((uint32_t)j / 3) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kRtLffCol0 + lb * kRtN;
+#pragma unroll
+      for (int g0 = 0; g0 < kRtN; g0 += 48) {
+        uint32_t v[48];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) tmem_ld16(taddr + g0 + 16 * i, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * i]));
+        tmem_ld_wait();
+        if (g0 == 48) {                                                // all 96 columns are in registers
+          tc_fence_before();
+          mbar_arrive_cluster(lffempty0 + lb * 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 48; ++i) v[i] = __shfl_down_sync(0xffffffffu, v[i], 1);   // accumulator row p holds pixel p-1
+        if (valid) {
+#pragma unroll
+          for (int kk = 0; kk < 6; ++kk) {
+            const uint4 rr4 = rbuf[g0 / 8 + kk];
+            const uint32_t rr[4] = {rr4.x, rr4.y, rr4.z, rr4.w};
+            uint32_t ow[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 g = rt_unpack_h2(rr[i]);
+              const int nn = g0 + 8 * kk + 2 * i;
+              ow[i] = rt_pack_h2((__uint_as_float(v[8 * kk + 2 * i]) + sb_lff[nn]) + g.x,
+                                 (__uint_as_float(v[8 * kk + 2 * i + 1]) + sb_lff[nn + 1]) + g.y);
+            }
+            const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + g0 / 8 + kk) * p.H + y) * p.W + x) * 8;
+            *reinterpret_cast<uint4*>(p.out + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
+        }
+      }
+    }
+  }
+
+  // ------------------------------------------------------------ teardown (the leader's MMAs touch the peer's smem / TMEM)
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 int make_p8_tmap(CUtensorMap* m, const bin_act_t& t, int box_rows);   // conv_igemm.cu
 
@@ -481,6 +786,15 @@ int launch_rdb_tail(const bin_act_t& x, int x_plane0, const bin_act_t& g, int g_
     p.dbg = g_dbg;
   }
 #endif
+  if (options().pair) {
+    static std::atomic<unsigned long long> opted_pair{0};   // per device
+    BIN_TRY(ensure_dynamic_smem(rdb_tail_pair_kernel, kRpSmem, opted_pair));
+    const int npt = (p.ntiles + 1) / 2, maxc = num_sms() / 2;
+    const int nclusters = npt < maxc ? npt : maxc;
+    rdb_tail_pair_kernel<<<2 * nclusters, 384, kRpSmem, s>>>(p);
+    BIN_CUDA_OK(cudaGetLastError());
+    return BIN_OK;
+  }
   auto kern = streams ? rdb_tail_kernel<true> : rdb_tail_kernel<false>;
   static std::atomic<unsigned long long> opted_streams{0}, opted_handoff{0};   // per device
   BIN_TRY(ensure_dynamic_smem(kern, kRtSmem, streams ? opted_streams : opted_handoff));
