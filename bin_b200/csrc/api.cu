@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <initializer_list>
 #include <string>
 #include <vector>
 
@@ -710,25 +711,33 @@ static int window_fwd_impl(const bin_net_t* net, const float* const* F, float* c
   const size_t bws_bytes = workspace_bytes - 9 * fbytes;
   float *p4 = tmp[0], *p6 = tmp[1], *p8 = tmp[2], *p5 = tmp[3], *p7 = tmp[4], *p6b = tmp[5];
   float *t0 = tmp[6], *t1 = tmp[7], *t2 = tmp[8];
-  auto lstm = [&](int k, const float* x, float* h) {
-    return launch_convlstm(x, nullptr, nullptr, net->lstm_w[k], net->lstm_b[k], h, nullptr, B, H, W, s);
+  // the cells of one recurrent hand-off are independent: one launch for all of them (grid.z = cell)
+  auto lstm = [&](int k0, int n, std::initializer_list<const float*> xs, std::initializer_list<float*> hs) {
+    LstmCells c;
+    memset(&c, 0, sizeof(c));
+    int i = 0;
+    for (const float* x : xs) c.x[i++] = x;
+    i = 0;
+    for (float* h : hs) c.h_out[i++] = h;
+    for (i = 0; i < n; ++i) { c.w[i] = net->lstm_w[k0 + i]; c.b[i] = net->lstm_b[k0 + i]; }
+    return launch_convlstm_multi(c, n, B, H, W, s);
   };
   // Stage 1 (RDN.py:371-374): 4 calls of step 0 + the one stage-1 call of step 1 that is not a repeat.
   BIN_TRY(run_stage(net, 0, 2, {{{F[0], F[1]}, o[0]}, {{F[1], F[2]}, o[1]}, {{F[2], F[3]}, o[2]},
                                {{F[3], F[4]}, o[3]}, {{F[4], F[5]}, o[10]}}, B, H, W, bws, bws_bytes, s, x3));
   // recurrent hand-off for the stage-1 outputs (RDN.py:451-453)
-  BIN_TRY(lstm(0, o[1], p4)); BIN_TRY(lstm(1, o[2], p6)); BIN_TRY(lstm(2, o[3], p8));
+  BIN_TRY(lstm(0, 3, {o[1], o[2], o[3]}, {p4, p6, p8}));
   // Stage 2: step 0 (RDN.py:384-386, "prev" slot duplicated) + step 1 (RDN.py:377-379) in ONE launch of 6 calls:
   // the step-1 calls only need stage-1 outputs and their ConvLSTM images, not step-0's stage 2.
   BIN_TRY(run_stage(net, 1, 3, {{{o[0], o[0], o[1]}, o[4]}, {{o[1], o[1], o[2]}, o[5]}, {{o[2], o[2], o[3]}, o[6]},
                                {{p4, o[1], o[2]}, t0}, {{p6, o[2], o[3]}, t1}, {{p8, o[3], o[10]}, o[11]}},
                     B, H, W, bws, bws_bytes, s, x3));
-  BIN_TRY(lstm(3, o[5], p5)); BIN_TRY(lstm(4, o[6], p7));                         // RDN.py:454-455
+  BIN_TRY(lstm(3, 2, {o[5], o[6]}, {p5, p7}));                                    // RDN.py:454-455
   // Stage 3: step 0 (RDN.py:387-388) + step 1 (RDN.py:380-381)
   BIN_TRY(run_stage(net, 2, 5, {{{o[4], F[1], o[4], o[5], F[2]}, o[7]}, {{o[5], F[2], o[5], o[6], F[3]}, o[8]},
                                {{p5, F[2], t0, t1, F[3]}, t2}, {{p7, F[3], t1, o[11], F[4]}, o[12]}},
                     B, H, W, bws, bws_bytes, s, x3));
-  BIN_TRY(lstm(5, o[8], p6b));                                                    // RDN.py:456
+  BIN_TRY(lstm(5, 1, {o[8]}, {p6b}));                                             // RDN.py:456
   // Stage 4: step 0 (RDN.py:389) + step 1 (RDN.py:382)
   BIN_TRY(run_stage(net, 3, 5, {{{o[1], o[1], o[7], o[8], o[2]}, o[9]}, {{p6b, o[2], t2, o[12], o[3]}, o[13]}},
                     B, H, W, bws, bws_bytes, s, x3));

@@ -269,53 +269,106 @@ __global__ void pack_bias_kernel(const float* __restrict__ b, int cout, int cout
 }
 
 // ------------------------------------------------------------------ K5: ConvLSTMCell (RDN.py:50-95)
-__global__ void convlstm_kernel(const float* __restrict__ x, const float* __restrict__ c_prev,
-                                const float* __restrict__ h_prev, const float* __restrict__ w,
-                                const float* __restrict__ bias, float* __restrict__ h_out, float* __restrict__ c_out,
-                                int B, int H, int W) {
-  __shared__ float sw[12 * 6 * 9];
+// g = Conv3x3(cat(x, h)) 6 -> 12 ; i,j,f,o = chunk(g,4) ; c' = c*sigmoid(f+1) + sigmoid(i)*tanh(j) ; h' = tanh(c')*sigmoid(o).
+// 648 FMA (324 when prev_state is None: h = 0 contributes nothing, RDN.py:57-68) and 15 transcendentals per pixel against
+// 36-60 bytes: arithmetic intensity 36 FLOP/B, above the fp32 CUDA-core ridge (~75 TFLOP/s / 6.5 TB/s = 11.5 FLOP/B) --
+// the kernel is FP32-FMA bound, so the design minimises instructions per FMA:
+//   * 64 x 16 pixel tile per 256-thread block; the (16+2) x (64+2) halo tile of every input channel is staged once in
+//     shared memory (zero fill = the conv's zero padding), so each input value is fetched from DRAM/L2 once;
+//   * each thread owns 4 consecutive pixels x 12 gate channels = 48 register accumulators; per (channel, ky) it reads its
+//     6 inputs with one 128-bit + one 64-bit shared load and per tap its 12 weights with three 128-bit broadcast loads:
+//     48 FMAs per 3 weight loads;
+//   * gates use ex2.approx-based sigmoid / tanh (|error| < 3e-7, two decades under the 1e-5 fp32 bar);
+//   * up to 3 independent cells (the cells of one recurrent hand-off, RDN.py:451-456) ride one launch in grid.z.
+constexpr int kLsTW = 64, kLsTH = 16, kLsPitch = 68;      // smem row: [x0-1 .. x0+64] at index 3.. -> pixel x0+k at index 4+k
+__device__ __forceinline__ float fast_sigmoid(float v) { return __frcp_rn(1.f + __expf(-v)); }
+__device__ __forceinline__ float fast_tanh(float v) { return 2.f * __frcp_rn(1.f + __expf(-2.f * v)) - 1.f; }
+
+template <bool STATE>
+__global__ void __launch_bounds__(256) convlstm_kernel(const __grid_constant__ LstmCells P, int B, int H, int W, int tiles_x,
+                                                       int tiles_y) {
+  constexpr int C = STATE ? 6 : 3;
+  __shared__ __align__(16) float sin_[C][kLsTH + 2][kLsPitch];
+  __shared__ __align__(16) float sw[C * 9 * 12];                 // [c][ky][kx][gate channel]
   __shared__ float sb[12];
-  for (int i = threadIdx.x; i < 12 * 6 * 9; i += blockDim.x) sw[i] = w[i];
-  if (threadIdx.x < 12) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
+  const int cell = blockIdx.z;
+  const float* __restrict__ w = P.w[cell];
+  for (int i = threadIdx.x; i < C * 9 * 12; i += 256) {
+    const int k = i % 12, t = (i / 12) % 9, c = i / 108;
+    sw[i] = w[(k * 6 + c) * 9 + t];                              // (12,6,3,3) OIHW
+  }
+  if (threadIdx.x < 12) sb[threadIdx.x] = P.b[cell][threadIdx.x];
+  int t = blockIdx.x;
+  const int txi = t % tiles_x; t /= tiles_x;
+  const int tyi = t % tiles_y;
+  const int b = t / tiles_y;
+  const int x0 = txi * kLsTW, y0 = tyi * kLsTH;
   const size_t hw = (size_t)H * W;
-  const size_t total = (size_t)B * hw;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int xw = i % W;
-    const int y = (i / W) % H;
-    const int b = i / hw;
-    float g[12];
+  // stage the halo tile: rows y0-1 .. y0+16, columns x0-1 .. x0+64 (index 3 .. 68 of the padded row)
+  for (int i = threadIdx.x; i < C * (kLsTH + 2) * (kLsTW + 2); i += 256) {
+    const int cx = i % (kLsTW + 2), r = (i / (kLsTW + 2)) % (kLsTH + 2), c = i / ((kLsTW + 2) * (kLsTH + 2));
+    const int yy = y0 + r - 1, xx = x0 + cx - 1;
+    float v = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const float* src = c < 3 ? P.x[cell] + ((size_t)b * 3 + c) * hw : P.h_prev[cell] + ((size_t)b * 3 + (c - 3)) * hw;
+      v = __ldg(src + (size_t)yy * W + xx);
+    }
+    sin_[c][r][3 + cx] = v;
+  }
+  __syncthreads();
+  const int tx4 = (threadIdx.x & 15) * 4, ty = threadIdx.x >> 4;
+  float acc[4][12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) g[k] = sb[k];
-    const int nin = h_prev ? 6 : 3;                         // h = 0 contributes nothing (RDN.py:57-68)
-    for (int c = 0; c < nin; ++c) {
-      const float* src = (c < 3 ? x + ((size_t)b * 3 + c) * hw : h_prev + ((size_t)b * 3 + (c - 3)) * hw);
+  for (int px = 0; px < 4; ++px)
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int yy = y + ky - 1;
-        if (yy < 0 || yy >= H) continue;
+    for (int k = 0; k < 12; ++k) acc[px][k] = sb[k];
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int xx = xw + kx - 1;
-          if (xx < 0 || xx >= W) continue;
-          const float v = src[(size_t)yy * W + xx];
+  for (int c = 0; c < C; ++c) {
 #pragma unroll
-          for (int k = 0; k < 12; ++k) g[k] = fmaf(sw[(k * 6 + c) * 9 + ky * 3 + kx], v, g[k]);
-        }
+    for (int ky = 0; ky < 3; ++ky) {
+      const float* row = &sin_[c][ty + ky][tx4];                 // row[3] = pixel tx4-1, row[4..7] = the 4 pixels, row[8] = +1
+      const float4 a = *reinterpret_cast<const float4*>(row + 4);
+      const float v[6] = {row[3], a.x, a.y, a.z, a.w, row[8]};
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4* wp = reinterpret_cast<const float4*>(&sw[((c * 3 + ky) * 3 + kx) * 12]);
+        const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        const float wk[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+        for (int px = 0; px < 4; ++px)
+#pragma unroll
+          for (int k = 0; k < 12; ++k) acc[px][k] = fmaf(wk[k], v[px + kx], acc[px][k]);
       }
     }
+  }
+  const int y = y0 + ty, x = x0 + tx4;
+  if (y >= H || x >= W) return;
+  const bool vec = ((W & 3) == 0) && (x + 3 < W);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {                            // i,j,f,o = chunk(4) (RDN.py:79)
-      const float gi = g[c], gj = g[3 + c], gf = g[6 + c], go = g[9 + c];
-      const float cp = c_prev ? c_prev[((size_t)b * 3 + c) * hw + (size_t)y * W + xw] : 0.f;
-      const float si = 1.f / (1.f + expf(-gi));
-      const float sf = 1.f / (1.f + expf(-(gf + 1.0f)));   // forget_bias = 1.0 (RDN.py:16,81)
-      const float so = 1.f / (1.f + expf(-go));
-      const float cn = cp * sf + si * tanhf(gj);
-      const float hn = tanhf(cn) * so;
-      const size_t off = ((size_t)b * 3 + c) * hw + (size_t)y * W + xw;
-      h_out[off] = hn;
-      if (c_out) c_out[off] = cn;
+  for (int c = 0; c < 3; ++c) {                                  // i,j,f,o = chunk(4) (RDN.py:79)
+    const size_t off = ((size_t)b * 3 + c) * hw + (size_t)y * W + x;
+    float cp[4] = {0.f, 0.f, 0.f, 0.f};
+    if (STATE) {
+      if (vec) { const float4 q = *reinterpret_cast<const float4*>(P.c_prev[cell] + off); cp[0] = q.x; cp[1] = q.y; cp[2] = q.z; cp[3] = q.w; }
+      else { for (int px = 0; px < 4; ++px) if (x + px < W) cp[px] = P.c_prev[cell][off + px]; }
+    }
+    float hn[4], cn[4];
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const float si = fast_sigmoid(acc[px][c]), sf = fast_sigmoid(acc[px][6 + c] + 1.0f);   // forget_bias = 1.0 (RDN.py:16,81)
+      const float so = fast_sigmoid(acc[px][9 + c]);
+      cn[px] = cp[px] * sf + si * fast_tanh(acc[px][3 + c]);
+      hn[px] = fast_tanh(cn[px]) * so;
+    }
+    if (vec) {
+      *reinterpret_cast<float4*>(P.h_out[cell] + off) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+      if (P.c_out[cell]) *reinterpret_cast<float4*>(P.c_out[cell] + off) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+    } else {
+      for (int px = 0; px < 4; ++px)
+        if (x + px < W) {
+          P.h_out[cell][off + px] = hn[px];
+          if (P.c_out[cell]) P.c_out[cell][off + px] = cn[px];
+        }
     }
   }
 }
@@ -719,13 +772,28 @@ int launch_pack_bias(const float* b, int cout, int cout_pad, float* dst, cudaStr
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
 }
-int launch_convlstm(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
-                    float* h_out, float* c_out, int B, int H, int W, cudaStream_t s) {
-  if ((c_prev == nullptr) != (h_prev == nullptr)) return fail(BIN_ERR_ARG, "convlstm: give both c_prev and h_prev or neither");
-  const size_t total = (size_t)B * H * W;
-  convlstm_kernel<<<grid_for(total, 128), 128, 0, s>>>(x, c_prev, h_prev, w, b, h_out, c_out, B, H, W);
+int launch_convlstm_multi(const LstmCells& cells, int ncells, int B, int H, int W, cudaStream_t s) {
+  if (ncells < 1 || ncells > 3) return fail(BIN_ERR_ARG, "convlstm: 1..3 cells per launch");
+  bool state = cells.h_prev[0] != nullptr;
+  for (int i = 0; i < ncells; ++i) {
+    if (!cells.x[i] || !cells.w[i] || !cells.b[i] || !cells.h_out[i]) return fail(BIN_ERR_ARG, "convlstm: null argument");
+    if ((cells.c_prev[i] == nullptr) != (cells.h_prev[i] == nullptr))
+      return fail(BIN_ERR_ARG, "convlstm: give both c_prev and h_prev or neither");
+    if ((cells.h_prev[i] != nullptr) != state) return fail(BIN_ERR_ARG, "convlstm: cells of one launch must all have or all lack a state");
+  }
+  const int tiles_x = (W + kLsTW - 1) / kLsTW, tiles_y = (H + kLsTH - 1) / kLsTH;
+  const dim3 grid((unsigned)(tiles_x * tiles_y * B), 1, (unsigned)ncells);
+  if (state) convlstm_kernel<true><<<grid, 256, 0, s>>>(cells, B, H, W, tiles_x, tiles_y);
+  else convlstm_kernel<false><<<grid, 256, 0, s>>>(cells, B, H, W, tiles_x, tiles_y);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
+}
+int launch_convlstm(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
+                    float* h_out, float* c_out, int B, int H, int W, cudaStream_t s) {
+  LstmCells c;
+  memset(&c, 0, sizeof(c));
+  c.x[0] = x; c.c_prev[0] = c_prev; c.h_prev[0] = h_prev; c.w[0] = w; c.b[0] = b; c.h_out[0] = h_out; c.c_out[0] = c_out;
+  return launch_convlstm_multi(c, 1, B, H, W, s);
 }
 int launch_p8_add(const bin_act_t& dst, int dplane0, const bin_act_t& src, int splane0, int nplanes, cudaStream_t s) {
   const size_t hw = (size_t)dst.H * dst.W;

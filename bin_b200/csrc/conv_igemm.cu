@@ -65,6 +65,7 @@ struct Ctrl {
   uint64_t wfull[kMaxResidentChunks];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t wready;            // PAIR: the peer's resident weight halves have landed (leader's copy is used)
   uint32_t tmem_base;
   volatile uint32_t issued;   // number of pipeline stages whose MMAs have been issued (MMA warp hand-off)
 };
@@ -125,9 +126,28 @@ __device__ __forceinline__ void split_store(__half* base_hi, __half* base_lo, co
   *reinterpret_cast<uint4*>(base_lo) = lo;
 }
 
-template <int NT, int KS, int EPI, bool SX, bool X3>
+// PAIR (cta_group::2, launched as (2,1,1) clusters; x-stacked resident-weight convs only): the two CTAs of a cluster each
+// run their own 256-pixel tile with their own producers, accumulators and epilogue warps, but the B operand -- the
+// resident weights -- is split between them (48 of the 96 rows of every slab per CTA) and ONE 256 x 96 x 16 MMA issued by
+// the leader's MMA warps feeds both: 5.5 KB instead of 7 KB of shared-memory operand traffic per SM and MMA (the limiter
+// of this kernel), and half the resident-weight footprint (two more ring slots for the 160-channel conv).
+// Barriers as in rdb_tail_pair_kernel: `full` in the leader (2 x bytes, both CTAs' TMA credit it), `empty` / `tmem_full`
+// by multicast commit into both CTAs, `tmem_empty` in the leader counting the epilogue threads of both CTAs.
+template <int NT, int KS, int EPI, bool SX, bool X3, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using C = ConvCfg<NT, KS, SX>;
+  static_assert(!PAIR || (SX && !X3 && EPI == BIN_EPI_P8), "the CTA-pair form exists for the x-stacked fp16 convs");
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  // tile sequence of this CTA: single CTA -> tiles blockIdx.x, +gridDim.x, ...; pair -> tile pair q = cluster, +nclusters, ...
+  // with tile 2q + rank (the peer of an odd tail re-runs the last tile with its stores suppressed)
+  const int tq0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tqstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tqn = PAIR ? (p.ntiles + 1) >> 1 : p.ntiles;
+  auto tile_at = [&](int tq, bool& live) {
+    int t = PAIR ? 2 * tq + (int)rank : tq;
+    live = t < p.ntiles;
+    return live ? t : p.ntiles - 1;
+  };
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
   float* sbias = reinterpret_cast<float*>(smem + 1024);
@@ -155,8 +175,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     for (int i = 0; i < kMaxResidentChunks; ++i) mbar_init(&ctrl->wfull[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctrl->tmem_full[i], 2);
-      mbar_init(&ctrl->tmem_empty[i], 256);
+      mbar_init(&ctrl->tmem_empty[i], PAIR ? 512 : 256);   // epilogue threads (of both CTAs)
     }
+    mbar_init(&ctrl->wready, 1);
     ctrl->issued = 0;
     fence_barrier_init();
   }
@@ -165,26 +186,41 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     for (int i = threadIdx.x; i < NT * p.nh; i += blockDim.x) sbias[i] = p.bias[i];
   const float* bsrc = bias_in_smem ? sbias : p.bias;
   if (warp == 2) {
-    tmem_alloc(&ctrl->tmem_base, C::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) { tmem_alloc_pair(&ctrl->tmem_base, C::TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(&ctrl->tmem_base, C::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();                      // both CTAs' barriers are initialised
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
+  constexpr int WH = PAIR ? 2 : 1;                             // resident B bytes per CTA = 1 / WH of the slab
+  constexpr int B_PLANE = C::NMMA * 16 / WH;                   // bytes of one 8-channel plane of a B slab in this CTA
 
   if ((warp == 0 || warp == 2) && lane == 0) {
     // ========================================================== TMA producers (stage i -> producer i%2)
     const uint32_t Y = warp >> 1;
     if (p.resident && Y == 0) {
       for (int c = 0; c < nchunks; ++c) {
-        mbar_expect_tx(&ctrl->wfull[c], C::W_CHUNK);
-        bulk_load_1d(res_w + c * C::W_CHUNK, reinterpret_cast<const uint8_t*>(p.w) + (size_t)c * C::W_CHUNK,
-                     C::W_CHUNK, &ctrl->wfull[c]);
+        mbar_expect_tx(&ctrl->wfull[c], C::W_CHUNK / WH);
+        if constexpr (PAIR) {                                  // this CTA's rows [48 r, 48 r + 48) of every plane of every tap
+          for (int tp = 0; tp < C::TAPS_C; ++tp)
+            for (int pl = 0; pl < kKPL; ++pl)
+              bulk_load_1d(res_w + c * (C::W_CHUNK / 2) + tp * (C::W_TAP / 2) + pl * B_PLANE,
+                           reinterpret_cast<const uint8_t*>(p.w) + (size_t)c * C::W_CHUNK + tp * C::W_TAP + pl * (C::NMMA * 16) +
+                               rank * B_PLANE,
+                           B_PLANE, &ctrl->wfull[c]);
+        } else {
+          bulk_load_1d(res_w + c * C::W_CHUNK, reinterpret_cast<const uint8_t*>(p.w) + (size_t)c * C::W_CHUNK,
+                       C::W_CHUNK, &ctrl->wfull[c]);
+        }
       }
     }
+    const uint32_t full0 = PAIR ? mapa_u32(smem_u32(&ctrl->full[0]), 0) : 0u;   // the LEADER's full barriers
     uint32_t it = 0, s = 0, ph = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int tq = tq0; tq < tqn; tq += tqstep) {
+      bool live;
+      const int tile = tile_at(tq, live);
       int t = tile;
       const int nh = t % p.nh; t /= p.nh;
       const int txi = t % p.tiles_x; t /= p.tiles_x;
@@ -199,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           mbar_wait(&ctrl->empty[s], ph ^ 1);
           if (Y == 0) dbg_rec(p, 0, it >> 1, 1);
           uint8_t* dst = stage0 + (size_t)s * stage_bytes;
-          mbar_expect_tx(&ctrl->full[s], (uint32_t)(nu * unit_bytes));
+          if (!PAIR || rank == 0) mbar_expect_tx(&ctrl->full[s], (uint32_t)((PAIR ? 2 : 1) * nu * unit_bytes));
           for (int u = 0; u < nu; ++u) {
             const int c = (unit + u) / C::NSUB, sub = (unit + u) % C::NSUB;
             const int lc = X3 ? c / 3 : c;                     // logical 32-channel chunk
@@ -207,7 +243,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             const void* tmap = seg1 ? (const void*)&p.tmap1 : (const void*)&p.tmap0;
             const int lplane = seg1 ? p.plane0_1 + (lc - p.nch0l) * kKPL : p.plane0_0 + lc * kKPL;
             const int plane = X3 ? 2 * lplane + ((c % 3) == 1 ? 4 : 0) : lplane;   // X3: hi, lo, hi again
-            tma_load_4d(dst + (size_t)u * unit_bytes, tmap, &ctrl->full[s], x0 * 8, y0 + (C::ROWSPLIT ? sub : 0), plane, b);
+            if constexpr (PAIR)
+              tma_load_4d_pair(dst + (size_t)u * unit_bytes, tmap, full0 + s * 8, x0 * 8, y0, plane, b);
+            else
+              tma_load_4d(dst + (size_t)u * unit_bytes, tmap, &ctrl->full[s], x0 * 8, y0 + (C::ROWSPLIT ? sub : 0), plane, b);
             if (!p.resident) {
               const size_t woff = ((size_t)(nh * nchunks + c) * C::TAPS_C + (C::ROWSPLIT ? sub * KS : 0)) * C::W_TAP;
               bulk_load_1d(dst + (size_t)u * unit_bytes + C::A_BYTES, reinterpret_cast<const uint8_t*>(p.w) + woff,
@@ -219,17 +258,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         if (++s == S) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1 || warp == 3) {
-    // ========================================================== MMA issuers (warp converged, one elected lane)
+  } else if (PAIR && warp == 1 && rank == 1) {
+    // ========================================================== peer: tell the leader when this CTA's B halves have landed
+    for (int c = 0; c < nchunks; ++c) mbar_wait(&ctrl->wfull[c], 0);
+    if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctrl->wready), 0));
+  } else if ((warp == 1 || warp == 3) && rank == 0) {
+    // ========================================================== MMA issuers (warp converged, one elected lane; PAIR: leader only)
     const uint32_t Y = warp >> 1;
-    constexpr uint32_t idesc = umma_idesc_f16(128, C::NMMA);
+    constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 256 : 128, C::NMMA);
     constexpr uint32_t D_HI = (128u >> 4) | (1u << 14);            // SBO=128 B, descriptor version 1
     constexpr uint32_t A_LBO = ((uint32_t)C::A_PLANE >> 4) << 16;
-    constexpr uint32_t B_LBO = ((uint32_t)(C::NMMA * 16) >> 4) << 16;
+    constexpr uint32_t B_LBO = ((uint32_t)B_PLANE >> 4) << 16;
     uint32_t it = 0, s = 0, ph = 0, tl = 0, dbg_it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tl) {
+    for (int tq = tq0; tq < tqn; tq += tqstep, ++tl) {
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-      mbar_wait(&ctrl->tmem_empty[as], aph ^ 1);
+      if constexpr (PAIR) mbar_wait_cluster(&ctrl->tmem_empty[as], aph ^ 1);
+      else mbar_wait(&ctrl->tmem_empty[as], aph ^ 1);
       tc_fence_after();
       int unit = 0;
       for (int j = 0; j < spt; ++j, ++it) {
@@ -241,6 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           if (p.resident && tl == 0) {
             for (int u = 0; u < nu; ++u)
               if ((unit + u) % C::NSUB == 0) mbar_wait(&ctrl->wfull[(unit + u) / C::NSUB], 0);
+            if (PAIR) mbar_wait_cluster(&ctrl->wready, 0);
           }
           while (ctrl->issued < it) __nanosleep(32);        // stage it-1 fully issued by the other warp (a tight
                                                             // shared-memory spin would compete with the MMA operand fetch)
@@ -251,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             const int c = (unit + u) / C::NSUB, sub = (unit + u) % C::NSUB;
             const uint32_t a_base = st_base + u * unit_bytes;
             const uint32_t w_base = p.resident
-                                        ? smem_u32(res_w + c * C::W_CHUNK) + (C::ROWSPLIT ? sub * KS * C::W_TAP : 0)
+                                        ? smem_u32(res_w + c * (C::W_CHUNK / WH)) + (C::ROWSPLIT ? sub * KS * C::W_TAP : 0)
                                         : a_base + C::A_BYTES;
             const uint32_t a_lo = ((a_base >> 4) & 0x3FFFu) | A_LBO;
             const uint32_t b_lo = ((w_base >> 4) & 0x3FFFu) | B_LBO;
@@ -268,15 +313,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 #pragma unroll
                   for (int jj = 0; jj < kKC / 16; ++jj) {
                     const uint64_t ad = ((uint64_t)D_HI << 32) | (a_lo + a_off + jj * 2 * (C::A_PLANE >> 4));
-                    const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + (tp * C::W_TAP + jj * 2 * C::NMMA * 16) / 16);
-                    umma_f16_ss(d, ad, bd, idesc, (tp == 0 && jj == 0) ? not_first : 1u);
+                    const uint64_t bd = ((uint64_t)D_HI << 32) | (b_lo + (tp * (C::W_TAP / WH) + jj * 2 * B_PLANE) / 16);
+                    if constexpr (PAIR) umma_f16_ss_pair(d, ad, bd, idesc, (tp == 0 && jj == 0) ? not_first : 1u);
+                    else umma_f16_ss(d, ad, bd, idesc, (tp == 0 && jj == 0) ? not_first : 1u);
                   }
                 }
               }
             }
             __syncwarp();
           }
-          if (elect_one()) umma_commit(&ctrl->empty[s]);   // frees the smem stage once these MMAs retire
+          if (elect_one()) {                               // frees the smem stage (in both CTAs) once these MMAs retire
+            if constexpr (PAIR) umma_commit_pair(&ctrl->empty[s]);
+            else umma_commit(&ctrl->empty[s]);
+          }
           tc_fence_before();                               // order this warp's tcgen05.mma before the flag (the
           __syncwarp();                                    // other warp pairs it with tc_fence_after above)
           if (lane == 0) ctrl->issued = it + 1;            // hand the tensor pipe to the other MMA warp
@@ -286,7 +335,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         unit += nu;
         if (++s == S) { s = 0; ph ^= 1; }
       }
-      if (elect_one()) umma_commit(&ctrl->tmem_full[as]);  // this warp's share of the tile's MMAs
+      if (elect_one()) {                                   // this warp's share of the tile's MMAs
+        if constexpr (PAIR) umma_commit_pair(&ctrl->tmem_full[as]);
+        else umma_commit(&ctrl->tmem_full[as]);
+      }
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -319,7 +371,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       }
     };
     frame_load(blockIdx.x, fv);
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++acc_it) {
+    const uint32_t tempty0 = PAIR ? mapa_u32(smem_u32(&ctrl->tmem_empty[0]), 0) : 0u;   // the LEADER's barriers
+    for (int tq = tq0; tq < tqn; tq += tqstep, ++acc_it) {
+      bool live;
+      const int tile = tile_at(tq, live);
       int t = tile;
       const int nh = t % p.nh; t /= p.nh;
       const int txi = t % p.tiles_x; t /= p.tiles_x;
@@ -341,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const int L = m * 128 + q * 32 + lane;
       const int ty = L >> 5, tx = L & 31;
       const int y = p.y0 + tyi * kTH + ty, x = txi * C::TW + tx;
-      const bool valid = (tx < C::TW) && (y < yend) && (x < p.W);
+      const bool valid = live && (tx < C::TW) && (y < yend) && (x < p.W);
       // operands of the epilogue that do not depend on the accumulators are fetched BEFORE waiting for
       // them, so their global-load latency overlaps the MMAs: the residual tile (RDN.py:165, :219) ...
       uint4 rbuf[(EPI == BIN_EPI_P8 && !SX) ? (X3 ? 2 : 1) * (NT / 8) : 1];
@@ -515,7 +570,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         }
       }
       tc_fence_before();
-      mbar_arrive(&ctrl->tmem_empty[as]);
+      if constexpr (PAIR) mbar_arrive_cluster(tempty0 + as * 8);
+      else mbar_arrive(&ctrl->tmem_empty[as]);
       if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 2);
     }
   }
@@ -523,9 +579,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   // ------------------------------------------------------------ teardown
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();                      // the leader's MMAs touch the peer's smem / TMEM
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -610,10 +668,14 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
   p.ntiles = nb * p.tiles_x * p.tiles_y * p.nh;
   p.relu = a.relu;
   const int nchunks = p.nch0 + p.nch1;
+  // CTA pairs (cta_group::2) for the x-stacked RDB convs: the resident weights are split between the two CTAs
+  constexpr bool kPairable = SX && KS == 3 && NT == 32 && EPI == BIN_EPI_P8 && !X3;
+  const int wh = (kPairable && options().pair) ? 2 : 1;
   // keep the whole weight set resident in smem when it leaves room for >= 3 activation stages
   p.resident = (p.nh == 1 && nchunks <= kMaxResidentChunks &&
-                kCtrlBytes + nchunks * C::W_CHUNK + 3 * C::A_BYTES + 256 <= kSmemMax) ? 1 : 0;
-  const int res_bytes = p.resident ? nchunks * C::W_CHUNK : 0;
+                kCtrlBytes + nchunks * C::W_CHUNK / wh + 3 * C::A_BYTES + 256 <= kSmemMax) ? 1 : 0;
+  const bool pair = wh == 2 && p.resident;
+  const int res_bytes = p.resident ? nchunks * C::W_CHUNK / (pair ? 2 : 1) : 0;
   const int unit_bytes = C::A_BYTES + (p.resident ? 0 : C::W_STAGE);
   const int nunits = nchunks * C::NSUB;
   // units per pipeline stage: an mbarrier round trip costs a few hundred cycles, so a stage should
@@ -642,6 +704,26 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
     p.dbg = g_dbg;
   }
 #endif
+  if constexpr (kPairable) {
+    if (pair) {
+      if (cps != 1) return fail(BIN_ERR_UNSUPPORTED, "conv pair kernel expects one unit per stage");
+      auto kp = conv_igemm_kernel<NT, KS, EPI, SX, X3, true>;
+      static std::atomic<unsigned long long> pair_opted{0};   // per device
+      BIN_TRY(ensure_dynamic_smem(kp, kSmemMax, pair_opted));
+      const int npt = (p.ntiles + 1) / 2, maxc = num_sms() / 2;
+      const int nclusters = npt < maxc ? npt : maxc;
+      if (nclusters < 1) return BIN_OK;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(2 * nclusters); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      BIN_CUDA_OK(cudaLaunchKernelEx(&cfg, kp, p));
+      return BIN_OK;
+    }
+  }
   auto kern = conv_igemm_kernel<NT, KS, EPI, SX, X3>;
   static std::atomic<unsigned long long> smem_opted{0};   // per instantiation, per device
   BIN_TRY(ensure_dynamic_smem(kern, kSmemMax, smem_opted));

@@ -84,6 +84,14 @@ extern long long* g_dbg;
 
 int launch_conv(const bin_conv_args_t& a, cudaStream_t s);
 
+// up to 3 independent ConvLSTM cells in one launch (aux_kernels.cu)
+struct LstmCells {
+  const float* x[3]; const float* c_prev[3]; const float* h_prev[3];
+  const float* w[3]; const float* b[3];
+  float* h_out[3]; float* c_out[3];
+};
+int launch_convlstm_multi(const LstmCells& cells, int ncells, int B, int H, int W, cudaStream_t s);
+
 // packed-weight geometry
 inline int conv_nt(int cout_pad) { return cout_pad % 96 == 0 ? 96 : (cout_pad > 128 ? 128 : cout_pad); }
 

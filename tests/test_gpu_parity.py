@@ -291,3 +291,29 @@ def test_fp32_mode_window_vs_oracle(net32, sd):
         outs = net32(*[f.cuda() for f in fr])
     worst = max((o.cpu() - r).abs().max().item() for o, r in zip(outs, ref))
     assert worst <= TOL_FP32_MODE, worst
+
+
+def test_cta_pair_kernels_bit_identical_to_single_cta():
+    """The cta_group::2 kernels (rdb_tail_pair_kernel, conv_igemm_kernel<...,PAIR>) keep the per-accumulator MMA order of
+    the single-CTA kernels: a whole window must hash identically under BIN_B200_PAIR=1 and =0 (the library reads the
+    switch once per process, hence two children).  Shapes: odd tile counts (dummy peer tile), many tiles per cluster."""
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys, hashlib; sys.path.insert(0, %r)\n"
+        "from oracle import bin_oracle as O\n"
+        "from bin_b200 import rdn\n"
+        "net = rdn.bin_stage4_lstm(); net.load_state_dict(O.synth_state_dict(0), strict=True); net = net.cuda().eval()\n"
+        "h = hashlib.sha256()\n"
+        "for (B, H, W) in [(1, 46, 122), (2, 136, 248), (1, 360, 640)]:\n"
+        "    fr = [f.cuda() for f in O.synth_frames(6, B, H, W, seed=5, smooth=True)]\n"
+        "    with torch.no_grad(): outs = net(*fr)\n"
+        "    for o in outs: h.update(o.cpu().numpy().tobytes())\n"
+        "print('HASH', h.hexdigest())\n" % ROOT)
+    got = {}
+    for pair in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BIN_B200_PAIR=pair), capture_output=True,
+                           text=True, timeout=900)
+        assert r.returncode == 0, (pair, r.stderr[-2000:])
+        got[pair] = r.stdout.strip().split("HASH")[-1].strip()
+    assert got["0"] == got["1"], got

@@ -19,7 +19,7 @@ tail -c 3000 gpurun_out/r02a_bench.json; tail -n 5 gpurun_out/r02a_bench.err
 ( time timeout 900 python bench.py --impl reference --steps 20 --warmup 5 ) > gpurun_out/r02a_bench_ref.json 2> gpurun_out/r02a_bench_ref.err
 cat gpurun_out/r02a_bench_ref.json; tail -n 5 gpurun_out/r02a_bench_ref.err
 # CTA-pair fused tail: numerics on ragged shapes first (watchdog traps instead of hanging), then the A/B timing
-BIN_B200_PAIR=1 timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "rdb_tail_bit or rdb_shapes" -p no:cacheprovider > gpurun_out/r02a_pair_pytest.log 2>&1
+BIN_B200_PAIR=1 timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "rdb_tail_bit or rdb_shapes or cta_pair" -p no:cacheprovider > gpurun_out/r02a_pair_pytest.log 2>&1
 tail -n 6 gpurun_out/r02a_pair_pytest.log
 timeout 600 python tools/ab_pair.py > gpurun_out/r02a_ab_pair.txt 2>&1
 cat gpurun_out/r02a_ab_pair.txt
