@@ -59,6 +59,14 @@ int launch_pack_frames(const bin_frames_t& fr, int H, int W, const bin_act_t& ds
 int launch_pack_weight(const float* w, int cout, int cin, int ks, int cout_pad, int cin_pad, int variant,
                        void* packed, cudaStream_t s, int x3 = 0);
 int launch_pack_bias(const float* b, int cout, int cout_pad, float* dst, cudaStream_t s);
+// batched packing: all tensors of one blob in one launch (aux_kernels.cu)
+void* pack_batch_new();
+int pack_batch_add_weight(void* hb, const float* w, int cout, int cin, int ks, int cout_pad, int cin_pad, int variant,
+                          void* packed, int x3);
+int pack_batch_add_weight_t(void* hb, const float* w, int cout, int cin, int ks, int row0, int nrows, int cout_pad_t,
+                            int cin_pad_t, void* packed);
+int pack_batch_add_bias(void* hb, const float* b, int cout, int cout_pad, float* dst);
+int pack_batch_launch(void* hb, cudaStream_t s);   // launches and frees the batch
 int launch_convlstm(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
                     float* h_out, float* c_out, int B, int H, int W, cudaStream_t s);
 int launch_pixel_loss_fwd(const float* const* a, const float* const* b, int npairs, size_t n, int kind, float eps,
@@ -615,18 +623,27 @@ int bin_convlstm_bwd(const float* x, const float* c_prev, const float* h_prev, c
 
 size_t bin_backbone_packed_bytes(int nframes) { return valid_nframes(nframes) ? backbone_layout(nframes).bytes : 0; }
 
+// all 66 weights + 66 biases of a backbone in ONE launch
+static int pack_backbone(int nframes, const float* const* w_host, const float* const* b_host, void* blob, int x3,
+                         cudaStream_t s) {
+  if (!w_host || !b_host || !blob) return fail(BIN_ERR_ARG, "backbone_pack: null argument");
+  const BackboneLayout L = backbone_layout(nframes, x3);
+  void* hb = pack_batch_new();
+  int rc = BIN_OK;
+  for (int i = 0; i < BIN_BACKBONE_NCONV && rc == BIN_OK; ++i) {
+    const ConvSpec& c = L.conv[i];
+    rc = pack_batch_add_weight(hb, w_host[i], c.cout, c.cin, c.ks, c.cout_pad, c.cin_pad, BIN_CONV_DEFAULT,
+                               (uint8_t*)blob + c.w_off, x3);
+    if (rc == BIN_OK) rc = pack_batch_add_bias(hb, b_host[i], c.cout, c.cout_pad, (float*)((uint8_t*)blob + c.b_off));
+  }
+  const int rl = pack_batch_launch(hb, s);      // always frees the batch
+  return rc != BIN_OK ? rc : rl;
+}
+
 int bin_backbone_pack(int nframes, const float* const* w_host, const float* const* b_host, void* blob,
                       bin_stream_t s) {
   if (!valid_nframes(nframes)) return fail(BIN_ERR_ARG, "backbone_pack: nframes must be 2, 3 or 5");
-  const BackboneLayout L = backbone_layout(nframes);
-  for (int i = 0; i < BIN_BACKBONE_NCONV; ++i) {
-    const ConvSpec& c = L.conv[i];
-    BIN_TRY(launch_pack_weight(w_host[i], c.cout, c.cin, c.ks, c.cout_pad, c.cin_pad, BIN_CONV_DEFAULT,
-                               (uint8_t*)blob + c.w_off,
-                               (cudaStream_t)s));
-    BIN_TRY(launch_pack_bias(b_host[i], c.cout, c.cout_pad, (float*)((uint8_t*)blob + c.b_off), (cudaStream_t)s));
-  }
-  return BIN_OK;
+  return pack_backbone(nframes, w_host, b_host, blob, 0, (cudaStream_t)s);
 }
 
 size_t bin_backbone_workspace_bytes(int nframes, int Btot, int H, int W) {
@@ -645,15 +662,20 @@ int bin_backbone_pack_t(int nframes, const float* const* w_host, void* blob_t, b
   if (!valid_nframes(nframes)) return fail(BIN_ERR_ARG, "backbone_pack_t: nframes must be 2, 3 or 5");
   const BackboneLayout L = backbone_layout(nframes);
   const BackboneLayoutT T = backbone_layout_t(nframes);
-  for (int i = 0; i < BIN_BACKBONE_NCONV; ++i) {
+  void* hb = pack_batch_new();
+  int rc = BIN_OK;
+  for (int i = 0; i < BIN_BACKBONE_NCONV && rc == BIN_OK; ++i) {
     const ConvSpec& c = L.conv[i];
     const TSpec* parts[2] = {&T.x[i], &T.g[i]};
     for (const TSpec* t : parts) {
-      if (t->nrows <= 0) continue;
-      BIN_TRY(launch_pack_weight_t(w_host[i], c.cout, c.cin, c.ks, t->row0, t->nrows, t->cout_pad_t, t->cin_pad_t,
-                                   (uint8_t*)blob_t + t->off, (cudaStream_t)s));
+      if (t->nrows <= 0 || rc != BIN_OK) continue;
+      rc = pack_batch_add_weight_t(hb, w_host[i], c.cout, c.cin, c.ks, t->row0, t->nrows, t->cout_pad_t, t->cin_pad_t,
+                                   (uint8_t*)blob_t + t->off);
     }
   }
+  const int rl = pack_batch_launch(hb, (cudaStream_t)s);
+  if (rc != BIN_OK) return rc;
+  BIN_TRY(rl);
   BIN_CUDA_OK(cudaMemsetAsync((uint8_t*)blob_t + T.zero_bias_off, 0, 1152 * sizeof(float), (cudaStream_t)s));
   return BIN_OK;
 }
@@ -759,15 +781,7 @@ size_t bin_backbone_packed_bytes_p(int nframes, int prec) { return valid_nframes
 int bin_backbone_pack_p(int nframes, const float* const* w_host, const float* const* b_host, void* blob, int prec,
                         bin_stream_t s) {
   if (!valid_nframes(nframes)) return fail(BIN_ERR_ARG, "backbone_pack: nframes must be 2, 3 or 5");
-  const int x3 = prec ? 1 : 0;
-  const BackboneLayout L = backbone_layout(nframes, x3);
-  for (int i = 0; i < BIN_BACKBONE_NCONV; ++i) {
-    const ConvSpec& c = L.conv[i];
-    BIN_TRY(launch_pack_weight(w_host[i], c.cout, c.cin, c.ks, c.cout_pad, c.cin_pad, BIN_CONV_DEFAULT,
-                               (uint8_t*)blob + c.w_off, (cudaStream_t)s, x3));
-    BIN_TRY(launch_pack_bias(b_host[i], c.cout, c.cout_pad, (float*)((uint8_t*)blob + c.b_off), (cudaStream_t)s));
-  }
-  return BIN_OK;
+  return pack_backbone(nframes, w_host, b_host, blob, prec ? 1 : 0, (cudaStream_t)s);
 }
 size_t bin_backbone_workspace_bytes_p(int nframes, int Btot, int H, int W, int prec) {
   return valid_nframes(nframes) ? backbone_ws(nframes, Btot, H, W, nullptr, false, prec ? 1 : 0).bytes : 0;

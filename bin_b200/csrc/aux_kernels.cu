@@ -41,33 +41,48 @@ __global__ void p8_to_nchw_kernel(const __half* __restrict__ src, int planes, in
 // ------------------------------------------------------------------ K3: frame concat + space-to-depth + cast
 // Reference: RDN.py:211/269/323 torch.cat(frames,1) then pixel_reshuffle(.,2) (RDN.py:107-132):
 // packed channel = (f*3+rgb)*4 + dy*2 + dx for pixel (2y+dy, 2x+dx); zero-padded to dst.planes*8.
-__global__ void pack_frames_kernel(const __grid_constant__ bin_frames_t fr, int H, int W, __half* __restrict__ dst,
-                                   int planes, int x3) {   // planes = LOGICAL planes; x3: dst holds hi/lo groups of 4
-  const int h = H / 2, w = W / 2;
-  const int Btot = fr.ncalls * fr.Bc;
-  const size_t total = (size_t)Btot * planes * h * w;
+// grid = (pixel groups, logical planes, batch); every thread packs kPkU output pixels of ONE 8-channel plane: all of its
+// 2 x 2 x kPkU 8-byte loads are issued before the first store (bytes in flight), index math is 32-bit, and consecutive
+// threads touch consecutive pixels (256-byte warp rows in, 512-byte warp rows out).
+constexpr int kPkU = 4;
+__global__ void __launch_bounds__(256) pack_frames_kernel(const __grid_constant__ bin_frames_t fr, int H, int W,
+                                                          __half* __restrict__ dst, int planes, int x3) {
+  // planes = LOGICAL planes; x3: dst holds hi/lo groups of 4
+  const int h = H >> 1, w = W >> 1;
+  const int hw = h * w;
+  const int pl = blockIdx.y, b = blockIdx.z;
+  const int call = b / fr.Bc, bb = b % fr.Bc;
   const int cin = 12 * fr.nframes;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int x = i % w;
-    const int y = (i / w) % h;
-    const int pl = (i / ((size_t)w * h)) % planes;
-    const int b = i / ((size_t)w * h * planes);
-    const int call = b / fr.Bc, bb = b % fr.Bc;
-    float fv[8];
+  const float* src[2];
 #pragma unroll
-    for (int half8 = 0; half8 < 2; ++half8) {          // 4 packed channels = one (frame, rgb) 2x2 patch
-      const int c4 = pl * 2 + half8;                   // index of the (f,rgb) pair
-      if (c4 * 4 < cin) {
-        const int f = c4 / 3, rgb = c4 % 3;
-        const float* src = fr.frame[call][f] + (((size_t)bb * 3 + rgb) * H + 2 * y) * W + 2 * x;
-        const float2 r0 = *reinterpret_cast<const float2*>(src);
-        const float2 r1 = *reinterpret_cast<const float2*>(src + W);
-        fv[half8 * 4 + 0] = r0.x; fv[half8 * 4 + 1] = r0.y; fv[half8 * 4 + 2] = r1.x; fv[half8 * 4 + 3] = r1.y;
+  for (int half8 = 0; half8 < 2; ++half8) {              // 4 packed channels = one (frame, rgb) 2x2 patch
+    const int c4 = pl * 2 + half8;                       // index of the (f,rgb) pair
+    src[half8] = (c4 * 4 < cin) ? fr.frame[call][c4 / 3] + ((size_t)bb * 3 + (c4 % 3)) * H * W : nullptr;
+  }
+  float2 r[kPkU][2][2];
+  int pos[kPkU];
+#pragma unroll
+  for (int u = 0; u < kPkU; ++u) {
+    pos[u] = (blockIdx.x * kPkU + u) * 256 + threadIdx.x;
+    const int y = pos[u] / w, x = pos[u] - y * w;
+#pragma unroll
+    for (int half8 = 0; half8 < 2; ++half8) {
+      if (src[half8] != nullptr && pos[u] < hw) {
+        const float* q = src[half8] + (size_t)(2 * y) * W + 2 * x;
+        r[u][half8][0] = __ldg(reinterpret_cast<const float2*>(q));
+        r[u][half8][1] = __ldg(reinterpret_cast<const float2*>(q + W));
       } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) fv[half8 * 4 + e] = 0.f;
+        r[u][half8][0] = r[u][half8][1] = make_float2(0.f, 0.f);
       }
     }
+  }
+  const int pplanes = x3 ? 2 * planes : planes;
+  const int pp = x3 ? 2 * (pl & ~3) + (pl & 3) : pl;
+  __half* base = dst + ((size_t)b * pplanes + pp) * hw * 8;
+#pragma unroll
+  for (int u = 0; u < kPkU; ++u) {
+    if (pos[u] >= hw) continue;
+    const float fv[8] = {r[u][0][0].x, r[u][0][0].y, r[u][0][1].x, r[u][0][1].y, r[u][1][0].x, r[u][1][0].y, r[u][1][1].x, r[u][1][1].y};
     __align__(16) __half v[8];
     __align__(16) __half vl[8];
 #pragma unroll
@@ -75,11 +90,8 @@ __global__ void pack_frames_kernel(const __grid_constant__ bin_frames_t fr, int 
       v[e] = __float2half_rn(fv[e]);
       vl[e] = __float2half_rn(fv[e] - __half2float(v[e]));
     }
-    const int pplanes = x3 ? 2 * planes : planes;
-    const int pp = x3 ? 2 * (pl & ~3) + (pl & 3) : pl;
-    const size_t off = ((((size_t)b * pplanes + pp) * h + y) * w + x) * 8;
-    *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(v);
-    if (x3) *reinterpret_cast<uint4*>(dst + off + (size_t)4 * h * w * 8) = *reinterpret_cast<const uint4*>(vl);
+    *reinterpret_cast<uint4*>(base + (size_t)pos[u] * 8) = *reinterpret_cast<const uint4*>(v);
+    if (x3) *reinterpret_cast<uint4*>(base + (size_t)pos[u] * 8 + (size_t)4 * hw * 8) = *reinterpret_cast<const uint4*>(vl);
   }
 }
 
@@ -89,13 +101,21 @@ __global__ void pack_frames_kernel(const __grid_constant__ bin_frames_t fr, int 
 // (a conv with V over dY gives dX for stride-1 / pad k/2 convs), co' < nrows, ci' < cout.
 // x3 != 0 (BIN_PREC_F32X3): three slabs per logical chunk -- hi, hi, lo of (w * 2^8) -- matching the kernel's
 // x_hi*W_hi + x_lo*W_hi + x_hi*W_lo chunk order.
-__global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, int ks, int cout_pad, int cin_pad,
-                                   int nt, int stackx, int transpose, int row0, int nrows, int x3,
-                                   __half* __restrict__ dst) {
+struct PackJob {            // one conv's weight tensor (or bias vector) of a batched pack launch
+  const float* src; void* dst;
+  int cout, cin, ks, cout_pad, cin_pad, nt, stackx, transpose, row0, nrows, x3, is_bias;
+  int block0, nblocks;     // this job's blocks are [block0, block0 + nblocks) of the launch
+};
+constexpr int kPackMaxJobs = 136;      // 66 weights + 66 biases (forward blob) / 66 + 48 transposed slabs, + slack
+struct PackBatch { PackJob job[kPackMaxJobs]; int njobs; };   // ~10 KB of kernel parameters (limit 32 KB)
+
+__device__ __forceinline__ void pack_weight_range(const float* __restrict__ w, int cout, int cin, int ks, int cout_pad, int cin_pad,
+                                                  int nt, int stackx, int transpose, int row0, int nrows, int x3,
+                                                  __half* __restrict__ dst, size_t first, size_t stride) {
   const int rep = x3 ? 3 : 1;
   const size_t total = (size_t)cout_pad * cin_pad * ks * ks * rep;
   const int nchunks = (cin_pad / kKC) * rep;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+  for (size_t i = first; i < total; i += stride) {
     size_t t = i;
     int e, kp, kx, ky, ch, co;
     e = t % 8; t /= 8;
@@ -127,6 +147,30 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
     } else {
       dst[i] = __float2half_rn(v);
     }
+  }
+}
+__global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, int ks, int cout_pad, int cin_pad,
+                                   int nt, int stackx, int transpose, int row0, int nrows, int x3,
+                                   __half* __restrict__ dst) {
+  pack_weight_range(w, cout, cin, ks, cout_pad, cin_pad, nt, stackx, transpose, row0, nrows, x3, dst,
+                    blockIdx.x * (size_t)blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+}
+// All conv weights + biases of one backbone in ONE launch (a training step re-packs 4 backbones x 2 layouts after every
+// optimizer step: 720 launches of the per-tensor kernel before).  Block -> job by binary search in the parameter table.
+__global__ void __launch_bounds__(256) pack_batch_kernel(const __grid_constant__ PackBatch P) {
+  int lo = 0, hi = P.njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (P.job[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackJob& j = P.job[lo];
+  const size_t first = (size_t)((int)blockIdx.x - j.block0) * 256 + threadIdx.x, stride = (size_t)j.nblocks * 256;
+  if (j.is_bias) {
+    float* d = reinterpret_cast<float*>(j.dst);
+    for (size_t i = first; i < (size_t)j.cout_pad; i += stride) d[i] = (int)i < j.cout ? j.src[i] : 0.f;
+  } else {
+    pack_weight_range(j.src, j.cout, j.cin, j.ks, j.cout_pad, j.cin_pad, j.nt, j.stackx, j.transpose, j.row0, j.nrows, j.x3,
+                      reinterpret_cast<__half*>(j.dst), first, stride);
   }
 }
 
@@ -737,8 +781,9 @@ int launch_pack_frames(const bin_frames_t& fr, int H, int W, const bin_act_t& ds
   const int lplanes = x3 ? dst.planes / 2 : dst.planes;
   if (dst.B != fr.ncalls * fr.Bc || dst.H != H / 2 || dst.W != W / 2 || lplanes * 8 < 12 * fr.nframes || (x3 && (lplanes & 3)))
     return fail(BIN_ERR_ARG, "pack_frames: destination geometry mismatch");
-  const size_t total = (size_t)dst.B * lplanes * dst.H * dst.W;
-  pack_frames_kernel<<<grid_for(total, 256), 256, 0, s>>>(fr, H, W, (__half*)dst.ptr, lplanes, x3);
+  const int hw = dst.H * dst.W;
+  const dim3 grid((unsigned)((hw + 256 * kPkU - 1) / (256 * kPkU)), (unsigned)lplanes, (unsigned)dst.B);
+  pack_frames_kernel<<<grid, 256, 0, s>>>(fr, H, W, (__half*)dst.ptr, lplanes, x3);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
 }
@@ -766,6 +811,61 @@ int launch_pack_weight_t(const float* w, int cout, int cin, int ks, int row0, in
                                                           (__half*)packed);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
+}
+// ---- batched packing (one launch per backbone blob)
+struct PackBatchHost { PackBatch b; int nblocks; };
+void* pack_batch_new() { PackBatchHost* h = new PackBatchHost; h->b.njobs = 0; h->nblocks = 0; return h; }
+static int pack_batch_add(void* hb, const PackJob& job, size_t total) {
+  PackBatchHost* h = static_cast<PackBatchHost*>(hb);
+  if (h->b.njobs >= kPackMaxJobs) return fail(BIN_ERR_UNSUPPORTED, "pack batch: too many tensors");
+  PackJob j = job;
+  size_t nb = (total + 256 * 8 - 1) / (256 * 8);               // ~8 elements per thread
+  if (nb < 1) nb = 1;
+  if (nb > 64) nb = 64;
+  j.block0 = h->nblocks; j.nblocks = (int)nb;
+  h->nblocks += (int)nb;
+  h->b.job[h->b.njobs++] = j;
+  return BIN_OK;
+}
+int pack_batch_add_weight(void* hb, const float* w, int cout, int cin, int ks, int cout_pad, int cin_pad, int variant,
+                          void* packed, int x3) {
+  if (cin_pad % kKC || cout_pad % 16 || cout > cout_pad || cin > cin_pad)
+    return fail(BIN_ERR_ARG, "pack_conv_weight: cin_pad must be a multiple of 32, cout_pad of 16");
+  const int nt = conv_nt(cout_pad);
+  if (cout_pad % nt) return fail(BIN_ERR_ARG, "pack_conv_weight: cout_pad must be <=128, or a multiple of 96 or 128");
+  PackJob j;
+  memset(&j, 0, sizeof(j));
+  j.src = w; j.dst = packed; j.cout = cout; j.cin = cin; j.ks = ks; j.cout_pad = cout_pad; j.cin_pad = cin_pad; j.nt = nt;
+  j.stackx = (ks == 3 && (cout_pad == 32 || cout_pad == 16) && variant == BIN_CONV_DEFAULT) ? 1 : 0;
+  j.x3 = x3;
+  return pack_batch_add(hb, j, (size_t)cout_pad * cin_pad * ks * ks * (x3 ? 3 : 1));
+}
+int pack_batch_add_weight_t(void* hb, const float* w, int cout, int cin, int ks, int row0, int nrows, int cout_pad_t,
+                            int cin_pad_t, void* packed) {
+  if (cin_pad_t % kKC || cout_pad_t % 96 || nrows > cout_pad_t || cout > cin_pad_t || row0 + nrows > cin)
+    return fail(BIN_ERR_ARG, "pack_conv_weight_t: bad padding / row range");
+  PackJob j;
+  memset(&j, 0, sizeof(j));
+  j.src = w; j.dst = packed; j.cout = cout; j.cin = cin; j.ks = ks; j.cout_pad = cout_pad_t; j.cin_pad = cin_pad_t; j.nt = 96;
+  j.transpose = 1; j.row0 = row0; j.nrows = nrows;
+  return pack_batch_add(hb, j, (size_t)cout_pad_t * cin_pad_t * ks * ks);
+}
+int pack_batch_add_bias(void* hb, const float* b, int cout, int cout_pad, float* dst) {
+  PackJob j;
+  memset(&j, 0, sizeof(j));
+  j.src = b; j.dst = dst; j.cout = cout; j.cout_pad = cout_pad; j.is_bias = 1;
+  return pack_batch_add(hb, j, (size_t)cout_pad);
+}
+int pack_batch_launch(void* hb, cudaStream_t s) {
+  PackBatchHost* h = static_cast<PackBatchHost*>(hb);
+  int rc = BIN_OK;
+  if (h->b.njobs > 0) {
+    pack_batch_kernel<<<h->nblocks, 256, 0, s>>>(h->b);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(BIN_ERR_CUDA, std::string("pack_batch_kernel: ") + cudaGetErrorString(e));
+  }
+  delete h;
+  return rc;
 }
 int launch_pack_bias(const float* b, int cout, int cout_pad, float* dst, cudaStream_t s) {
   pack_bias_kernel<<<(cout_pad + 127) / 128, 128, 0, s>>>(b, cout, cout_pad, dst);
