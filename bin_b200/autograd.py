@@ -67,8 +67,11 @@ class BackboneStageFn(torch.autograd.Function):
         dev = ctx.save.device
         with torch.cuda.device(dev):
             gouts = [torch.zeros((B, 3, H, W), device=dev) if g is None else g.contiguous().float() for g in gouts]
-            gmax = torch.stack([g.abs().amax() for g in gouts]).amax().clamp_min(1e-30)
-            scale = torch.exp2(torch.floor(torch.log2(LOSS_SCALE_TARGET / gmax))).reshape(1).float()   # stays on device
+            sbuf = torch.empty(2, device=dev)                                    # [scale, scratch]; stays on the device
+            gp = (C.c_void_p * ncalls)(*[g.data_ptr() for g in gouts])
+            check(lib().bin_grad_scale(gp, ncalls, gouts[0].numel(), LOSS_SCALE_TARGET, sbuf.data_ptr(),
+                                       sbuf.data_ptr() + 4, _stream()))
+            scale = sbuf[:1]
             dframes = [[torch.empty((B, 3, H, W), device=dev) for _ in range(n)] for _ in range(ncalls)]
             dout = ops.make_frames([[g] * n for g in gouts], gouts)             # only .out / ncalls / Bc are read
             dfr = ops.make_frames(dframes, [None] * ncalls)

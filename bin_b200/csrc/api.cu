@@ -59,6 +59,8 @@ int launch_pack_frames(const bin_frames_t& fr, int H, int W, const bin_act_t& ds
 int launch_pack_weight(const float* w, int cout, int cin, int ks, int cout_pad, int cin_pad, int variant,
                        void* packed, cudaStream_t s, int x3 = 0);
 int launch_pack_bias(const float* b, int cout, int cout_pad, float* dst, cudaStream_t s);
+int launch_grad_scale(const float* const* gouts, int n, size_t numel, float target, float* scale_dev, unsigned* tmp_dev,
+                      cudaStream_t s);
 // batched packing: all tensors of one blob in one launch (aux_kernels.cu)
 void* pack_batch_new();
 int pack_batch_add_weight(void* hb, const float* w, int cout, int cin, int ks, int cout_pad, int cin_pad, int variant,
@@ -699,6 +701,12 @@ int bin_backbone_bwd(int nframes, const void* blob_t, const bin_frames_t* dout, 
     return fail(BIN_ERR_ARG, "backbone_bwd: null argument");
   return run_backbone_bwd(nframes, blob_t, *dout, *dframes, H, W, save_ws, grad_ws_ptr, grad_ws_bytes, grad_params,
                           scale_dev, (cudaStream_t)s);
+}
+
+int bin_grad_scale(const float* const* gouts_host, int n, size_t numel, float target, float* scale_dev, void* tmp4_dev,
+                   bin_stream_t s) {
+  if (!gouts_host || !scale_dev || !tmp4_dev) return fail(BIN_ERR_ARG, "grad_scale: null argument");
+  return launch_grad_scale(gouts_host, n, numel, target, scale_dev, (unsigned*)tmp4_dev, (cudaStream_t)s);
 }
 
 int bin_rdb_fwd(const void* blob, int nframes, int index, const float* x, float* y, int B, int h, int w,

@@ -278,17 +278,22 @@ __global__ void grad_out_to_p8_kernel(const __grid_constant__ bin_frames_t dout,
   }
 }
 // db[c] += inv_scale * sum over (B, H, W) of dY[c] for P8 planes [plane0, plane0+ceil(C/8)).
-__global__ void p8_bias_grad_kernel(const __half* __restrict__ dy, int planes, int plane0, int C, int B, size_t hw,
-                                    const float* __restrict__ scale, float* __restrict__ db) {
+// grid = (pixel groups, planes, batch): no 64-bit div/mod per element, 4 independent 16-byte loads in flight per thread
+__global__ void __launch_bounds__(256) p8_bias_grad_kernel(const __half* __restrict__ dy, int planes, int plane0, int C, int hw,
+                                                           const float* __restrict__ scale, float* __restrict__ db) {
   __shared__ float part[8][8];
-  const int pl = blockIdx.y;                        // plane within the range
+  const int pl = blockIdx.y, b = blockIdx.z;
+  const __half* base = dy + ((size_t)b * planes + plane0 + pl) * (size_t)hw * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const size_t total = (size_t)B * hw;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t px = i % hw;
-    const int b = i / hw;
-    const uint4 v = *reinterpret_cast<const uint4*>(dy + (((size_t)b * planes + plane0 + pl) * hw + px) * 8);
-    const __half* h8 = reinterpret_cast<const __half*>(&v);
+  uint4 v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int px = (blockIdx.x * 4 + u) * 256 + threadIdx.x;
+    v[u] = px < hw ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)px * 8)) : make_uint4(0, 0, 0, 0);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const __half* h8 = reinterpret_cast<const __half*>(&v[u]);
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] += __half2float(h8[k]);
   }
@@ -300,11 +305,30 @@ __global__ void p8_bias_grad_kernel(const __half* __restrict__ dy, int planes, i
     for (int k = 0; k < 8; ++k) part[warp][k] = acc[k];
   __syncthreads();
   if (threadIdx.x < 8) {
-    float s = 0.f;
-    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += part[wv][threadIdx.x];
+    float sum = 0.f;
+    for (int wv = 0; wv < 8; ++wv) sum += part[wv][threadIdx.x];
     const int c = pl * 8 + threadIdx.x;
-    if (c < C) atomicAdd(db + c, s / scale[0]);
+    if (c < C) atomicAdd(db + c, sum / scale[0]);
   }
+}
+
+// ---- loss scale of a backbone's backward (autograd.py): scale = 2^floor(log2(target / max|dOut|)), kept on the device
+struct GradPtrs { const float* p[BIN_MAX_CALLS]; int n; };
+__global__ void __launch_bounds__(256) grad_absmax_kernel(const __grid_constant__ GradPtrs G, size_t numel, unsigned* __restrict__ bits) {
+  const float* g = G.p[blockIdx.y];
+  float m = 0.f;
+  const size_t n4 = numel / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(numel & 3)) m = fmaxf(m, fabsf(g[n4 * 4 + threadIdx.x]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(bits, __float_as_uint(m));     // non-negative floats order like their bit patterns
+}
+__global__ void grad_scale_finalize_kernel(const unsigned* __restrict__ bits, float target, float* __restrict__ scale) {
+  const float gmax = fmaxf(__uint_as_float(*bits), 1e-30f);
+  *scale = exp2f(floorf(log2f(target / gmax)));
 }
 
 __global__ void pack_bias_kernel(const float* __restrict__ b, int cout, int cout_pad, float* __restrict__ dst) {
@@ -928,9 +952,27 @@ int launch_grad_out_to_p8(const bin_frames_t& dout, int H, int W, const bin_act_
   return BIN_OK;
 }
 int launch_bias_grad(const bin_act_t& dy, int plane0, int C, const float* scale, float* db, cudaStream_t s) {
-  const size_t hw = (size_t)dy.H * dy.W;
-  dim3 grid(64, (C + 7) / 8);
-  p8_bias_grad_kernel<<<grid, 256, 0, s>>>((const __half*)dy.ptr, dy.planes, plane0, C, dy.B, hw, scale, db);
+  const int hw = dy.H * dy.W;
+  dim3 grid((unsigned)((hw + 1023) / 1024), (unsigned)((C + 7) / 8), (unsigned)dy.B);
+  p8_bias_grad_kernel<<<grid, 256, 0, s>>>((const __half*)dy.ptr, dy.planes, plane0, C, hw, scale, db);
+  BIN_CUDA_OK(cudaGetLastError());
+  return BIN_OK;
+}
+int launch_grad_scale(const float* const* gouts, int n, size_t numel, float target, float* scale_dev, unsigned* tmp_dev,
+                      cudaStream_t s) {
+  if (n < 1 || n > BIN_MAX_CALLS) return fail(BIN_ERR_ARG, "grad_scale: 1..BIN_MAX_CALLS tensors");
+  GradPtrs G;
+  memset(&G, 0, sizeof(G));
+  G.n = n;
+  for (int i = 0; i < n; ++i) {
+    if (!gouts[i] || (reinterpret_cast<uintptr_t>(gouts[i]) & 15)) return fail(BIN_ERR_ARG, "grad_scale: null or unaligned gradient");
+    G.p[i] = gouts[i];
+  }
+  BIN_CUDA_OK(cudaMemsetAsync(tmp_dev, 0, sizeof(unsigned), s));
+  const dim3 grid((unsigned)grid_for(numel / 4 + 1, 256), (unsigned)n);
+  grad_absmax_kernel<<<grid, 256, 0, s>>>(G, numel, tmp_dev);
+  BIN_CUDA_OK(cudaGetLastError());
+  grad_scale_finalize_kernel<<<1, 1, 0, s>>>(tmp_dev, target, scale_dev);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
 }

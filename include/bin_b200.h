@@ -174,6 +174,11 @@ size_t bin_backbone_grad_param_floats(int nframes);          /* fp32 [w0,b0,w1,b
 int bin_backbone_bwd(int nframes, const void* blob_t, const bin_frames_t* dout, const bin_frames_t* dframes, int H, int W,
                      const void* save_ws, void* grad_ws, size_t grad_ws_bytes, float* grad_params,
                      const float* scale_dev, bin_stream_t s);
+/* Loss scale for one backbone backward: *scale_dev = 2^floor(log2(target / max_k max|gouts[k]|)) (a power of two, so
+ * scaling and un-scaling are exact), computed on the device -- no host synchronisation.  gouts_host: host array of n
+ * (<= BIN_MAX_CALLS) device pointers to fp32 tensors of `numel` elements, 16-byte aligned; tmp4_dev: 4 bytes of scratch. */
+int bin_grad_scale(const float* const* gouts_host, int n, size_t numel, float target, float* scale_dev, void* tmp4_dev,
+                   bin_stream_t s);
 
 /* Unit-test entry: one RDB (RDN.py:149-165) on fp32 NCHW (B,96,h,w), using RDB `index` of the blob. */
 int bin_rdb_fwd(const void* blob, int nframes, int index, const float* x, float* y, int B, int h, int w,
