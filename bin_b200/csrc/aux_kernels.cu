@@ -348,7 +348,7 @@ __global__ void pack_bias_kernel(const float* __restrict__ b, int cout, int cout
 //     48 FMAs per 3 weight loads;
 //   * gates use ex2.approx-based sigmoid / tanh (|error| < 3e-7, two decades under the 1e-5 fp32 bar);
 //   * up to 3 independent cells (the cells of one recurrent hand-off, RDN.py:451-456) ride one launch in grid.z.
-constexpr int kLsTW = 64, kLsTH = 16, kLsPitch = 68;      // smem row: [x0-1 .. x0+64] at index 3.. -> pixel x0+k at index 4+k
+constexpr int kLsTW = 64, kLsTH = 16, kLsPitch = 72;      // smem row: [x0-1 .. x0+64] at index 3..68 -> pixel x0+k at index 4+k
 __device__ __forceinline__ float fast_sigmoid(float v) { return __frcp_rn(1.f + __expf(-v)); }
 __device__ __forceinline__ float fast_tanh(float v) { return 2.f * __frcp_rn(1.f + __expf(-2.f * v)) - 1.f; }
 

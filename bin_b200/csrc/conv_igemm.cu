@@ -161,8 +161,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   const int spt = (nunits + cps - 1) / cps;                   // stages per tile
   const int unit_bytes = C::A_BYTES + (p.resident ? 0 : C::W_STAGE);
   const int stage_bytes = cps * unit_bytes;
+  constexpr int WH = PAIR ? 2 : 1;                             // resident B bytes per CTA = 1 / WH of the slab
+  constexpr int B_PLANE = C::NMMA * 16 / WH;                   // bytes of one 8-channel plane of a B slab in this CTA
   uint8_t* res_w = smem + kCtrlBytes;
-  uint8_t* stage0 = res_w + (p.resident ? nchunks * C::W_CHUNK : 0);
+  uint8_t* stage0 = res_w + (p.resident ? nchunks * (C::W_CHUNK / WH) : 0);
 
   // ------------------------------------------------------------ one-time setup
   if (threadIdx.x == 0) {
@@ -194,8 +196,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   if constexpr (PAIR) cluster_sync_all();                      // both CTAs' barriers are initialised
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
-  constexpr int WH = PAIR ? 2 : 1;                             // resident B bytes per CTA = 1 / WH of the slab
-  constexpr int B_PLANE = C::NMMA * 16 / WH;                   // bytes of one 8-channel plane of a B slab in this CTA
 
   if ((warp == 0 || warp == 2) && lane == 0) {
     // ========================================================== TMA producers (stage i -> producer i%2)

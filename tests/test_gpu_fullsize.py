@@ -152,8 +152,11 @@ def test_adam_step_is_seen_by_the_next_forward(sd):
     with torch.no_grad():
         ya, yb = a(*fr), b(*fr)                                           # graphed inference after the steps
     assert max((p - q).abs().max().item() for p, q in zip(ya, yb)) <= 2e-3
+    # Adam normalises every gradient to a +-lr step: an element whose (tiny) gradient differs in sign between the two
+    # runs (atomics in the bias gradients are not bit-reproducible) moves 2 lr apart per step -- bound: 3 steps x 2 lr
     for p, q in zip(a.parameters(), b.parameters()):
-        assert (p - q).abs().max().item() <= 1e-4
+        d = (p - q).abs()
+        assert d.max().item() <= 6.5e-4 and d.mean().item() <= 5e-6
 
 
 def _oracle_window_grads_gpu(fr, cots, sd, dtype=torch.float32):
