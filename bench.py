@@ -138,7 +138,7 @@ def pick_cpu_threads(run, budget_s=20.0):
     ncpu = os.cpu_count() or 1
     fr = O.synth_frames(6, 1, 192, 320, seed=1)
     best, sweep, t_start = None, {}, time.perf_counter()
-    for th in [t for t in (8, 16, 32, 64, 128) if t <= ncpu] or [ncpu]:
+    for th in [t for t in (8, 16, 32, 64) if t <= ncpu] or [ncpu]:
         torch.set_num_threads(th)
         run([f[:, :, :32, :32].contiguous() for f in fr])               # thread-pool / primitive warm-up
         t0 = time.perf_counter()
@@ -147,7 +147,7 @@ def pick_cpu_threads(run, budget_s=20.0):
         sweep[th] = round(dt, 3)
         if best is None or dt < best[1]:
             best = (th, dt)
-        if time.perf_counter() - t_start > budget_s:
+        if time.perf_counter() - t_start > budget_s or dt > 1.3 * best[1]:      # past the sweet spot: more threads only hurt
             break
     torch.set_num_threads(best[0])
     return best[0], sweep

@@ -372,16 +372,31 @@ __global__ void __launch_bounds__(256) convlstm_kernel(const __grid_constant__ L
   const int b = t / tiles_y;
   const int x0 = txi * kLsTW, y0 = tyi * kLsTH;
   const size_t hw = (size_t)H * W;
-  // stage the halo tile: rows y0-1 .. y0+16, columns x0-1 .. x0+64 (index 3 .. 68 of the padded row)
-  for (int i = threadIdx.x; i < C * (kLsTH + 2) * (kLsTW + 2); i += 256) {
-    const int cx = i % (kLsTW + 2), r = (i / (kLsTW + 2)) % (kLsTH + 2), c = i / ((kLsTW + 2) * (kLsTH + 2));
-    const int yy = y0 + r - 1, xx = x0 + cx - 1;
-    float v = 0.f;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-      const float* src = c < 3 ? P.x[cell] + ((size_t)b * 3 + c) * hw : P.h_prev[cell] + ((size_t)b * 3 + (c - 3)) * hw;
-      v = __ldg(src + (size_t)yy * W + xx);
+  // stage the halo tile: rows y0-1 .. y0+16, columns x0-1 .. x0+64 (index 3 .. 68 of the padded row).  The trip count is a
+  // compile-time constant and all loads of a batch are issued before the first shared-memory store, so a thread has up
+  // to 14 global loads in flight (a dependent load->store loop ran at one DRAM round trip per element).
+  constexpr int kElems = C * (kLsTH + 2) * (kLsTW + 2), kIt = (kElems + 255) / 256, kBatch = 14;
+  static_assert(kIt % kBatch == 0, "staging batches");
+#pragma unroll 1
+  for (int it0 = 0; it0 < kIt; it0 += kBatch) {
+    float v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = (it0 + u) * 256 + threadIdx.x;
+      const int cx = i % (kLsTW + 2), r = (i / (kLsTW + 2)) % (kLsTH + 2), c = i / ((kLsTW + 2) * (kLsTH + 2));
+      const int yy = y0 + r - 1, xx = x0 + cx - 1;
+      v[u] = 0.f;
+      if (i < kElems && yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const float* src = c < 3 ? P.x[cell] + ((size_t)b * 3 + c) * hw : P.h_prev[cell] + ((size_t)b * 3 + (c - 3)) * hw;
+        v[u] = __ldg(src + (size_t)yy * W + xx);
+      }
     }
-    sin_[c][r][3 + cx] = v;
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = (it0 + u) * 256 + threadIdx.x;
+      const int cx = i % (kLsTW + 2), r = (i / (kLsTW + 2)) % (kLsTH + 2), c = i / ((kLsTW + 2) * (kLsTH + 2));
+      if (i < kElems) sin_[c][r][3 + cx] = v[u];
+    }
   }
   __syncthreads();
   const int tx4 = (threadIdx.x & 15) * 4, ty = threadIdx.x >> 4;

@@ -12,6 +12,8 @@ H, W = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (720, 1280
 net = rdn.bin_stage4_lstm()
 net.load_state_dict(O.synth_state_dict(0), strict=True)
 net = net.cuda().eval()
+if "--fp32" in sys.argv:
+    rdn.set_precision(net, "fp32")
 fr = [f.cuda() for f in O.synth_frames(6, 1, H, W, seed=1234, smooth=True)]
 with torch.no_grad():
     for i in range(n):
