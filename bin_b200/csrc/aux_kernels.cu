@@ -353,7 +353,7 @@ __device__ __forceinline__ float fast_sigmoid(float v) { return __frcp_rn(1.f + 
 __device__ __forceinline__ float fast_tanh(float v) { return 2.f * __frcp_rn(1.f + __expf(-2.f * v)) - 1.f; }
 
 template <bool STATE>
-__global__ void __launch_bounds__(256) convlstm_kernel(const __grid_constant__ LstmCells P, int B, int H, int W, int tiles_x,
+__global__ void __launch_bounds__(256, 3) convlstm_kernel(const __grid_constant__ LstmCells P, int B, int H, int W, int tiles_x,
                                                        int tiles_y) {
   constexpr int C = STATE ? 6 : 3;
   __shared__ __align__(16) float sin_[C][kLsTH + 2][kLsPitch];

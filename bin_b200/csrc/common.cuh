@@ -49,12 +49,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// `tag` identifies the waiter in the watchdog message (kernel instantiation / role / iteration), 0 = untagged.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned long long tag = 0ull) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > BIN_SPIN_LIMIT) {
-      printf("bin_b200: mbarrier watchdog (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x,
-             (void*)bar, parity);
+      printf("bin_b200: mbarrier watchdog (block %d/%d thread %d bar %p parity %u tag %llx)\n", blockIdx.x, gridDim.x,
+             threadIdx.x, (void*)bar, parity, tag);
       __trap();
     }
   }

@@ -98,9 +98,9 @@ constexpr int kThreads = 384;   // 12 warps, see the role table below
 //   warp 1        : MMA issuer  A  (accumulator 0)              warp 3 : MMA issuer B (accumulator 1)
 //   warps 4..11   : epilogue, warp w handles TMEM lane quarter w%4 of accumulator tile (w-4)/4
 // One ring of S (even) smem stages; stage i is filled by producer i%2 and its MMAs are issued by MMA
-// warp i%2.  Both MMA warps observe EVERY full barrier in order (a waiter may never fall two phases
-// behind a parity-tracked mbarrier) and hand the tensor pipe to each other through a shared-memory
-// counter, so one warp's barrier poll / descriptor setup overlaps the other's issue phase.  The two
+// warp i%2, which is also the only waiter of that stage's full barrier.  The two MMA warps hand the
+// tensor pipe to each other through a shared-memory counter (strict stage order), so one warp's
+// barrier poll / descriptor setup overlaps the other's issue phase.  The two
 // TMEM accumulator buffers alternate per tile and are released by the epilogue (tmem_full counts
 // one tcgen05.commit per MMA warp).
 // A pipeline stage holds up to p.cps "units" (unit = one 32-channel chunk, or one (chunk, ky) for 5x5).
@@ -143,6 +143,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   const int tq0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tqstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int tqn = PAIR ? (p.ntiles + 1) >> 1 : p.ntiles;
+  // watchdog tag: instantiation | role | pipeline iteration
+  constexpr unsigned long long kTag = ((unsigned long long)NT << 48) | ((unsigned long long)KS << 44) | ((unsigned long long)EPI << 40) |
+                                      ((unsigned long long)SX << 38) | ((unsigned long long)X3 << 37) | ((unsigned long long)PAIR << 36);
   auto tile_at = [&](int tq, bool& live) {
     int t = PAIR ? 2 * tq + (int)rank : tq;
     live = t < p.ntiles;
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const int nu = (nunits - unit < cps) ? nunits - unit : cps;
         if ((it & 1u) == Y) {
           if (Y == 0) dbg_rec(p, 0, it >> 1, 0);
-          mbar_wait(&ctrl->empty[s], ph ^ 1);
+          mbar_wait(&ctrl->empty[s], ph ^ 1, kTag | (1ull << 32) | it);
           if (Y == 0) dbg_rec(p, 0, it >> 1, 1);
           uint8_t* dst = stage0 + (size_t)s * stage_bytes;
           if (!PAIR || rank == 0) mbar_expect_tx(&ctrl->full[s], (uint32_t)((PAIR ? 2 : 1) * nu * unit_bytes));
@@ -273,15 +276,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     for (int tq = tq0; tq < tqn; tq += tqstep, ++tl) {
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
       if constexpr (PAIR) mbar_wait_cluster(&ctrl->tmem_empty[as], aph ^ 1);
-      else mbar_wait(&ctrl->tmem_empty[as], aph ^ 1);
+      else mbar_wait(&ctrl->tmem_empty[as], aph ^ 1, kTag | (3ull << 32) | tl);
       tc_fence_after();
       int unit = 0;
       for (int j = 0; j < spt; ++j, ++it) {
         const int nu = (nunits - unit < cps) ? nunits - unit : cps;
         const bool mine = (it & 1u) == Y;
         if (mine && Y == 0 && lane == 0) dbg_rec(p, 1, dbg_it, 0);
-        mbar_wait(&ctrl->full[s], ph);                      // both warps observe every phase
         if (mine) {
+          // Each MMA warp waits ONLY on the stages it issues (S is even, so stage parity = warp): a parity-tracked
+          // mbarrier must never be waited on by a thread that can fall a whole phase behind -- mbarrier.try_wait may
+          // suspend the thread, and a waiter that wakes after the barrier completed TWO phases sees "not complete" and
+          // hangs.  (Both warps used to observe every full barrier; the warp that only observed could be lapped while
+          // suspended: a rare watchdog under load, seen once at 720p in the split-fp16 mode.)  Ordering between the two
+          // warps is carried by ctrl->issued alone.
+          mbar_wait(&ctrl->full[s], ph, kTag | (2ull << 32) | it);
           if (p.resident && tl == 0) {
             for (int u = 0; u < nu; ++u)
               if ((unit + u) % C::NSUB == 0) mbar_wait(&ctrl->wfull[(unit + u) / C::NSUB], 0);
@@ -415,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       }
       constexpr float kAcc = X3 ? (1.f / 256.f) : 1.f;      // X3 weights are packed scaled by 2^8
       if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 0);
-      mbar_wait(&ctrl->tmem_full[as], aph);
+      mbar_wait(&ctrl->tmem_full[as], aph, kTag | (4ull << 32) | acc_it);
       if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + m * C::NMMA;

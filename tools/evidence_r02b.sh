@@ -2,8 +2,11 @@
 # Round-2 evidence bundle B (run under gpurun, 1 GPU): CTA-pair kernels -- numerics, A/B, ncu before/after, launch list.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/r02b_gpu.txt
-# 1. numerics of everything that touches the pair kernels (default = pair on)
-( time timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_conv_fuzz.py tests/test_gpu_streaming.py -q -x -p no:cacheprovider ) > gpurun_out/r02b_pytest_pair.log 2>&1
+# 0. the whole GPU suite in one process (pair kernels off by default)
+( time timeout 2400 python -m pytest tests -m gpu -q -s -p no:cacheprovider ) > gpurun_out/r02b_pytest.log 2>&1
+tail -n 12 gpurun_out/r02b_pytest.log; grep -a "watchdog\|\[bwd\|\[fullsize\|\[weights" gpurun_out/r02b_pytest.log
+# 1. numerics of everything that touches the pair kernels, with the pair kernels on
+( time BIN_B200_PAIR=1 timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_conv_fuzz.py tests/test_gpu_streaming.py -q -p no:cacheprovider ) > gpurun_out/r02b_pytest_pair.log 2>&1
 tail -n 8 gpurun_out/r02b_pytest_pair.log
 # 2. A/B timings in separate processes
 timeout 600 python tools/ab_pair.py > gpurun_out/r02b_ab_pair.txt 2>&1; cat gpurun_out/r02b_ab_pair.txt
