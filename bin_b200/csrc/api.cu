@@ -26,6 +26,9 @@ static Options read_options() {
   o.fuse_lff = !((e = env("BIN_B200_FUSE_LFF")) && *e == '0');
   o.tail_streams = !((e = env("BIN_B200_TAIL_STREAMS")) && *e == '0');
   o.pair = (e = env("BIN_B200_PAIR")) && *e == '1';     // CTA-pair kernels: opt-in until verified on hardware
+  o.msplit = (e = env("BIN_B200_MSPLIT")) && *e == '1';
+  o.stage_mmas = (e = env("BIN_B200_STAGE_MMAS")) ? atoi(e) : 12;
+  if (o.stage_mmas < 1) o.stage_mmas = 12;
   o.band_budget = (e = env("BIN_B200_BAND_BUDGET_KB")) ? (size_t)atoll(e) << 10 : (~(size_t)0 >> 1);
   return o;
 }

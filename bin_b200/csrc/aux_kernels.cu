@@ -409,9 +409,9 @@ __global__ void __launch_bounds__(256, 3) convlstm_kernel(const __grid_constant_
   for (int c = 0; c < C; ++c) {
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const float* row = &sin_[c][ty + ky][tx4];                 // row[3] = pixel tx4-1, row[4..7] = the 4 pixels, row[8] = +1
-      const float4 a = *reinterpret_cast<const float4*>(row + 4);
-      const float v[6] = {row[3], a.x, a.y, a.z, a.w, row[8]};
+      const float4* row = reinterpret_cast<const float4*>(&sin_[c][ty + ky][tx4]);   // [3] = pixel tx4-1, [4..7] = the 4 pixels, [8] = +1
+      const float4 lo = row[0], a = row[1], hi = row[2];         // three conflict-free 128-bit loads (scalar loads at a
+      const float v[6] = {lo.w, a.x, a.y, a.z, a.w, hi.x};       // 4-word thread stride were 2-way bank conflicts)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const float4* wp = reinterpret_cast<const float4*>(&sw[((c * 3 + ky) * 3 + kx) * 12]);

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     if (p.nch1 > 0) tma_prefetch_desc(&p.tmap1);
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&ctrl->full[i], 1);
-      mbar_init(&ctrl->empty[i], 1);
+      mbar_init(&ctrl->empty[i], p.msplit ? 2 : 1);        // M-split: both MMA warps consume every stage
     }
     for (int i = 0; i < kMaxResidentChunks; ++i) mbar_init(&ctrl->wfull[i], 1);
     for (int i = 0; i < 2; ++i) {
@@ -281,7 +281,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       int unit = 0;
       for (int j = 0; j < spt; ++j, ++it) {
         const int nu = (nunits - unit < cps) ? nunits - unit : cps;
-        const bool mine = (it & 1u) == Y;
+        // Two ways to share the tensor pipe between the two MMA warps:
+        //  * stage alternation (msplit = 0): warp it%2 issues ALL MMAs of stage `it`, then hands the pipe over through
+        //    ctrl->issued -- every hand-off is a bubble of a few hundred cycles (in situ 64-75 cycles per N=96 MMA against
+        //    56 in isolation);
+        //  * M-split (msplit = 1): both warps consume EVERY stage, warp Y issues only the MMAs of accumulator Y (tile rows
+        //    128 Y .. 128 Y + 127).  The two accumulators are independent, so nothing orders the warps against each other
+        //    (no hand-off, no shared counter); a stage is recycled when both have committed (empty count 2), so neither
+        //    waiter can be lapped.  The per-accumulator MMA order is unchanged -> bit-identical results.
+        const bool mine = p.msplit ? true : (it & 1u) == Y;
         if (mine && Y == 0 && lane == 0) dbg_rec(p, 1, dbg_it, 0);
         if (mine) {
           // Each MMA warp waits ONLY on the stages it issues (S is even, so stage parity = warp): a parity-tracked
@@ -296,7 +304,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
               if ((unit + u) % C::NSUB == 0) mbar_wait(&ctrl->wfull[(unit + u) / C::NSUB], 0);
             if (PAIR) mbar_wait_cluster(&ctrl->wready, 0);
           }
-          while (ctrl->issued < it) __nanosleep(32);        // stage it-1 fully issued by the other warp (a tight
+          if (!p.msplit)
+            while (ctrl->issued < it) __nanosleep(32);      // stage it-1 fully issued by the other warp (a tight
                                                             // shared-memory spin would compete with the MMA operand fetch)
           if (Y == 0 && lane == 0) dbg_rec(p, 1, dbg_it, 1);
           tc_fence_after();
@@ -313,6 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             if (elect_one()) {
 #pragma unroll
               for (int m = 0; m < kMT; ++m) {
+                if (p.msplit && (uint32_t)m != Y) continue;
                 const uint32_t d = tmem_base + as * C::ACC_COLS + m * C::NMMA;
 #pragma unroll
                 for (int tp = 0; tp < C::TAPS_S; ++tp) {
@@ -337,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           }
           tc_fence_before();                               // order this warp's tcgen05.mma before the flag (the
           __syncwarp();                                    // other warp pairs it with tc_fence_after above)
-          if (lane == 0) ctrl->issued = it + 1;            // hand the tensor pipe to the other MMA warp
+          if (lane == 0 && !p.msplit) ctrl->issued = it + 1;   // hand the tensor pipe to the other MMA warp
           if (Y == 0 && lane == 0) dbg_rec(p, 1, dbg_it, 2);
           ++dbg_it;
         }
@@ -690,7 +700,7 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
   // units per pipeline stage: an mbarrier round trip costs a few hundred cycles, so a stage should
   // carry >= ~12 MMAs (>= ~700 tensor-pipe cycles); one 1x1 unit is only 4 MMAs.
   const int mma_per_unit = kMT * C::TAPS_S * (kKC / 16);
-  int cps = (12 + mma_per_unit - 1) / mma_per_unit;
+  int cps = (options().stage_mmas + mma_per_unit - 1) / mma_per_unit;
   if (cps > nunits) cps = nunits;
   const int avail = kSmemMax - kCtrlBytes - res_bytes - 256;
   while (cps > 1 && avail / (cps * unit_bytes) < 2) --cps;
@@ -706,6 +716,7 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
   p.res = reinterpret_cast<const __half*>(a.res.ptr); p.res_planes = a.res.planes; p.res_plane0 = a.res_plane0;
   p.fr = a.fr;
   p.debug = options().debug;
+  p.msplit = options().msplit ? 1 : 0;
 #ifdef BIN_B200_TOOLS
   if (p.debug & 8) {
     if (!g_dbg) { BIN_CUDA_OK(cudaMalloc(&g_dbg, 3 * 4096 * sizeof(long long))); }

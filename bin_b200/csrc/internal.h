@@ -48,7 +48,9 @@ struct Options {
   int debug;                 // BIN_B200_DEBUG   bit 3: role timeline (tools build only), bit 4: synchronise after each conv launch
   bool fuse_lff;             // BIN_B200_FUSE_LFF=0 runs conv3 and LFF as two launches instead of rdb_tail_kernel
   bool tail_streams;         // BIN_B200_TAIL_STREAMS=0 selects the hand-off variant of rdb_tail_kernel
-  bool pair;                 // BIN_B200_PAIR=0 disables the CTA-pair (cta_group::2) kernels
+  bool pair;                 // BIN_B200_PAIR=1 selects the CTA-pair (cta_group::2) kernels (measured slower: opt-in)
+  bool msplit;               // BIN_B200_MSPLIT: conv MMA warps split the tile's two accumulators instead of alternating stages
+  int stage_mmas;            // BIN_B200_STAGE_MMAS: target MMAs per pipeline stage of the conv kernel (default 12)
   size_t band_budget;        // BIN_B200_BAND_BUDGET_KB (L2 band walker; default: one band)
 };
 const Options& options();
@@ -74,7 +76,7 @@ struct alignas(64) ConvParams {
   int H, W, Btot;                      // conv resolution
   int b0, y0, ny;                      // batch / row sub-range processed by this launch
   int tiles_x, tiles_y, ntiles, nh;    // nh = cout_pad / NT
-  int relu, resident, nstages, cps, debug;
+  int relu, resident, nstages, cps, debug, msplit;
   __half* out; int out_planes, out_plane0, store_planes;
   const __half* res; int res_planes, res_plane0;
   bin_frames_t fr;

@@ -123,26 +123,44 @@ def space_to_depth2(x: Tensor) -> Tensor:
 
 
 _EMULATE_FP16 = False      # tests only: round weights / stored activations to fp16 like the CUDA path stores them
+_EMULATE_FP16_GRADS = False
 
 
 class emulate_fp16_storage:
     """Context manager: the oracle rounds conv weights and every tensor the CUDA path stores in fp16
     (packed input, each conv's stored output) to fp16 precision (straight-through for autograd).  Used by the
-    backward tests to separate kernel errors from ReLU sign flips caused by fp16-vs-fp32 forward differences."""
+    backward tests to separate kernel errors from ReLU sign flips caused by fp16-vs-fp32 forward differences.
+    grads=True additionally rounds the GRADIENT of every such tensor to fp16 after power-of-two loss scaling, which
+    is how the CUDA backward stores dY between layers (bin_b200/autograd.py: scale = 2^floor(log2(2048 / max|g|)))."""
+
+    def __init__(self, grads: bool = False):
+        self.grads = grads
 
     def __enter__(self):
-        global _EMULATE_FP16
-        self.prev, _EMULATE_FP16 = _EMULATE_FP16, True
+        global _EMULATE_FP16, _EMULATE_FP16_GRADS
+        self.prev = (_EMULATE_FP16, _EMULATE_FP16_GRADS)
+        _EMULATE_FP16, _EMULATE_FP16_GRADS = True, self.grads
 
     def __exit__(self, *a):
-        global _EMULATE_FP16
-        _EMULATE_FP16 = self.prev
+        global _EMULATE_FP16, _EMULATE_FP16_GRADS
+        _EMULATE_FP16, _EMULATE_FP16_GRADS = self.prev
+
+
+def _round_grad_fp16(g: Tensor) -> Tensor:
+    m = g.abs().max()
+    if not torch.isfinite(m) or m == 0:
+        return g
+    s = torch.exp2(torch.floor(torch.log2(2048.0 / m)))
+    return (g * s).half().to(g.dtype) / s
 
 
 def _q(t: Tensor) -> Tensor:
     if not _EMULATE_FP16:
         return t
-    return t + (t.half().float() - t).detach()
+    out = t + (t.half().to(t.dtype) - t).detach()
+    if _EMULATE_FP16_GRADS and out.requires_grad:
+        out.register_hook(_round_grad_fp16)
+    return out
 
 
 def conv(x: Tensor, sd: SD, name: str) -> Tensor:

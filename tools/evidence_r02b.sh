@@ -14,7 +14,7 @@ for pair in 0 1; do BIN_B200_PAIR=$pair timeout 300 python tools/fusion_bound.py
 for pair in 0 1 0 1; do BIN_B200_PAIR=$pair timeout 300 python tools/run_window.py 6 --graph 2>&1 | tail -n 4 | sed "s/^/pair=$pair /" >> gpurun_out/r02b_window_ab.txt; done; cat gpurun_out/r02b_window_ab.txt
 # 3. ncu: launch list of one steady-state window (pair on), then --set full of the two RDB kernels, pair off / on
 export BIN_B200_GRAPH=0
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -s 230 -c 222 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -s 227 -c 223 --csv \
     --log-file gpurun_out/r02b_launches_window.csv python tools/run_window.py 2 > gpurun_out/r02b_ncu_launch.log 2>&1
 tail -n 2 gpurun_out/r02b_ncu_launch.log
 for pair in 0 1; do

@@ -15,15 +15,16 @@ os.makedirs(P, exist_ok=True)
 
 
 def short(name):
-    m = re.search(r"conv_igemm_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d)(?:, (?:\(bool\))?\d)?>", name)
+    m = re.search(r"conv_igemm_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d)(?:, (?:\(bool\))?(\d))?(?:, (?:\(bool\))?(\d))?>", name)
     if m:
         epi = {"0": "P8", "1": "PIXSHUF", "2": "FINAL"}[m.group(3)]
-        return f"conv_igemm<NT={m.group(1)},KS={m.group(2)},{epi},SX={m.group(4)}>"
+        pair = ",PAIR" if m.group(6) == "1" else ""
+        return f"conv_igemm<NT={m.group(1)},KS={m.group(2)},{epi},SX={m.group(4)}{pair}>"
     return re.sub(r"\(.*", "", name).replace("binb::", "").replace("void ", "")
 
 
-def launches():
-    path = os.path.join(G, "launches_window.csv")
+def launches(csvname="launches_window.csv", outname=None, cmd_note=None):
+    path = os.path.join(G, csvname)
     if not os.path.exists(path):
         return
     lines = [l for l in open(path) if not l.startswith("==")]
@@ -38,10 +39,10 @@ def launches():
         a[0] += 1
         a[1] += v
         tot += v
-    with open(os.path.join(P, f"{tag}_launches_window.md"), "w") as f:
-        f.write(f"# {tag}: ncu launch list of ONE steady-state 6-frame 1280x720 window\n\n"
-                f"Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s {528 + len(rows)} -c {len(rows)} --csv python tools/run_window.py 2`\n"
-                f"(BIN_B200_GRAPH=0; skip = 528 weight-pack launches + the {len(rows)} launches of window 0). Per-launch times under ncu are\n"
+    with open(os.path.join(P, outname or f"{tag}_launches_window.md"), "w") as f:
+        f.write(f"# {tag}: ncu launch list of ONE steady-state 6-frame 1280x720 window\n\n" +
+                (cmd_note or (f"Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s {528 + len(rows)} -c {len(rows)} --csv python tools/run_window.py 2`\n"
+                f"(BIN_B200_GRAPH=0; skip = 528 weight-pack launches + the {len(rows)} launches of window 0).")) + " Per-launch times under ncu are\n"
                 "cold-cache and serialised: compare SHARES, not absolutes.\n\n"
                 f"launches: {len(rows)}, sum of kernel durations: {tot/1e3:.2f} ms\n\n| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -60,7 +61,7 @@ WANT = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram r
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %")]
 
 
-def full(rep, title, note):
+def full(rep, title, note, extra=()):
     path = os.path.join(G, rep)
     if not os.path.exists(path):
         return
@@ -71,22 +72,42 @@ def full(rep, title, note):
     with open(os.path.join(P, f"{tag}_{rep.replace('.ncu-rep','')}.md"), "w") as f:
         f.write(f"# {tag}: {title}\n\n{note}\n\n| metric | " + " | ".join(short(d[ix['Kernel Name']]) for d in data) + " |\n")
         f.write("|---|" + "---|" * len(data) + "\n")
-        for m, label in WANT:
+        for m, label in list(WANT) + list(extra):
             if m in ix:
                 f.write(f"| {label} [{units[ix[m]]}] | " + " | ".join(d[ix[m]][:12] for d in data) + " |\n")
     print("wrote", rep)
 
 
-launches()
-full("prof_rdb5.ncu-rep", "ncu --set full: RDB 5 of the stage-1 launch (5 batched calls, 360x640): conv0..conv3 (x-stacked) + LFF",
-     "Command: `ncu --set full --clock-control none --import-source on -k regex:conv_igemm_kernel -s 357 -c 5 python tools/run_window.py 2`.\n"
-     "Algorithmic bytes per launch: conv c reads 5*230400*(192+64c) B and writes 5*230400*64 B; LFF reads 5*230400*640 B, writes 5*230400*192 B.\n"
-     "Algorithmic FLOPs per launch: 2*5*230400*(96+32c)*32*9 (conv c), 2*5*230400*224*96 (LFF).")
-full("prof_wgrad.ncu-rep", "ncu --set full: weight-gradient GEMM (tcgen05 MN-major) inside a training step, batch 4 x 256x256",
-     "Command: `BT_STEPS=1 BT_WARM=1 ncu --set full --clock-control none --import-source on -k regex:wgrad_kernel -s 300 -c 2 python tools/bench_train.py 4 256 256` (captured before the slab-reduce flush replaced the atomics).")
-full("prof_tail.ncu-rep", "ncu --set full: tail of the same stage: GFF.0, GFF.1, UPNet.0(+PixelShuffle), UPNet.2(+mean)",
-     "Command: `ncu --set full --clock-control none --import-source on -k regex:conv_igemm_kernel -s 392 -c 4 python tools/run_window.py 2`.")
-full("prof_rdb_tail.ncu-rep", "ncu --set full: fused RDB tail (conv3 3x3+ReLU, LFF 1x1, residual) of the stage-1 launch (5 batched calls, 360x640)",
-     "Command: `ncu --set full --clock-control none --import-source on -k regex:rdb_tail_kernel -s 48 -c 2 python tools/run_window.py 2`.\n"
-     "Algorithmic bytes per launch: reads 5*230400*384 B (x + g0..g2) + 5*230400*192 B (residual, L2-resident), writes 5*230400*192 B.\n"
-     "Algorithmic FLOPs per launch: 2*5*230400*(192*32*9 + 224*96).")
+if tag == "r01":
+    launches()
+    full("prof_rdb5.ncu-rep", "ncu --set full: RDB 5 of the stage-1 launch (5 batched calls, 360x640): conv0..conv3 (x-stacked) + LFF",
+         "Command: `ncu --set full --clock-control none --import-source on -k regex:conv_igemm_kernel -s 357 -c 5 python tools/run_window.py 2`.\n"
+         "Algorithmic bytes per launch: conv c reads 5*230400*(192+64c) B and writes 5*230400*64 B; LFF reads 5*230400*640 B, writes 5*230400*192 B.\n"
+         "Algorithmic FLOPs per launch: 2*5*230400*(96+32c)*32*9 (conv c), 2*5*230400*224*96 (LFF).")
+    full("prof_wgrad.ncu-rep", "ncu --set full: weight-gradient GEMM (tcgen05 MN-major) inside a training step, batch 4 x 256x256",
+         "Command: `BT_STEPS=1 BT_WARM=1 ncu --set full --clock-control none --import-source on -k regex:wgrad_kernel -s 300 -c 2 python tools/bench_train.py 4 256 256` (captured before the slab-reduce flush replaced the atomics).")
+    full("prof_tail.ncu-rep", "ncu --set full: tail of the same stage: GFF.0, GFF.1, UPNet.0(+PixelShuffle), UPNet.2(+mean)",
+         "Command: `ncu --set full --clock-control none --import-source on -k regex:conv_igemm_kernel -s 392 -c 4 python tools/run_window.py 2`.")
+    full("prof_rdb_tail.ncu-rep", "ncu --set full: fused RDB tail (conv3 3x3+ReLU, LFF 1x1, residual) of the stage-1 launch (5 batched calls, 360x640)",
+         "Command: `ncu --set full --clock-control none --import-source on -k regex:rdb_tail_kernel -s 48 -c 2 python tools/run_window.py 2`.\n"
+         "Algorithmic bytes per launch: reads 5*230400*384 B (x + g0..g2) + 5*230400*192 B (residual, L2-resident), writes 5*230400*192 B.\n"
+         "Algorithmic FLOPs per launch: 2*5*230400*(192*32*9 + 224*96).")
+
+if tag == "r02":
+    launches("r02b_launches_window.csv", "r02_launches_window.md",
+             "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 227 -c 223 --csv python tools/run_window.py 2` "
+             "(BIN_B200_GRAPH=0; skip = 4 batched weight-pack launches + the 223 launches of window 0; CTA-pair kernels on).")
+    FP = [("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe % of peak"),
+          ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots active %"),
+          ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts")]
+    full("r02a2_prof_k345.ncu-rep", "ncu --set full: the memory-/FP32-bound kernels of one window: K3 pack_frames, K5 convlstm, (K4 = final conv, see r02_prof_final)",
+         "Command: `ncu --set full --clock-control none --import-source on -k regex:'pack_frames_kernel|convlstm_kernel|conv_igemm_kernel<16' -s 4 -c 6 python tools/run_window.py 2`.\n"
+         "pack_frames: reads 3n fp32 frames (24n B per low-res position; frames shared by adjacent calls hit L2), writes 16 B per 8-channel plane.\n"
+         "convlstm (prev_state=None): 324 FMA + 15 transcendentals per pixel against 36 B -> FP32-FMA bound, not HBM bound (DESIGN 4d).", FP)
+    for pr in ("0", "1"):
+        full(f"r02b_prof_tail_pair{pr}.ncu-rep", f"ncu --set full: fused RDB tail at 5x360x640, BIN_B200_PAIR={pr} ({'CTA-pair cta_group::2' if pr == '1' else 'single-CTA'} kernel), same box",
+             f"Command: `BIN_B200_PAIR={pr} ncu --set full --clock-control none --import-source on -k regex:rdb_tail -s 48 -c 1 python tools/run_window.py 2`.\n"
+             "Algorithmic bytes per launch: reads 5*230400*384 B (x + g0..g2) + residual (L2), writes 5*230400*192 B; FLOPs 2*5*230400*(192*32*9 + 224*96).")
+        full(f"r02b_prof_conv_pair{pr}.ncu-rep", f"ncu --set full: x-stacked RDB convs 0..2 at 5x360x640, BIN_B200_PAIR={pr}, same box",
+             f"Command: `BIN_B200_PAIR={pr} ncu --set full --clock-control none --import-source on -k regex:'conv_igemm_kernel<32' -s 144 -c 3 python tools/run_window.py 2`.\n"
+             "Algorithmic FLOPs per launch: 2*5*230400*(96+32c)*32*9; bytes: reads 5*230400*(192+64c), writes 5*230400*64.")
