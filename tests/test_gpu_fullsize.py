@@ -199,7 +199,9 @@ def test_window_backward_b2_256_vs_fp16_storage_oracle(sd):
     net = rdn.bin_stage4_lstm(); net.load_state_dict(sd, strict=True); net = net.cuda().train()
     frg = [f.cuda().requires_grad_(True) for f in fr]
     outs = net(*frg)
-    assert max((o.detach() - r).abs().max().item() for o, r in zip(outs, ref_outs)) <= TOL_FP16
+    fwd = max((o.detach() - r).abs().max().item() for o, r in zip(outs, ref_outs))
+    print(f"[bwd 2x256x256] forward max-abs vs the fp16-storage oracle: {fwd:.3e}")
+    assert fwd <= TOL_FP16
     sum((o * c.cuda()).sum() for o, c in zip(outs, cots)).backward()
     for k in range(6):
         err = (frg[k].grad - gfr[k]).abs().max().item() / gfr[k].abs().max().item()

@@ -50,8 +50,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         res["window_ms"] = round(t(lambda: net(*fr), reps=10), 3)
     print(json.dumps(res))
 else:
-    cfgs = [{"BIN_B200_MSPLIT": "0"}, {"BIN_B200_MSPLIT": "1"}, {"BIN_B200_MSPLIT": "0", "BIN_B200_STAGE_MMAS": "24"},
-            {"BIN_B200_MSPLIT": "1", "BIN_B200_STAGE_MMAS": "24"}, {"BIN_B200_MSPLIT": "0"}, {"BIN_B200_MSPLIT": "1"}]
+    cfgs = [{"BIN_B200_MSPLIT": "0"}, {"BIN_B200_MSPLIT": "1"}, {"BIN_B200_MSPLIT": "1", "BIN_B200_STAGE_MMAS": "24"},
+            {"BIN_B200_MSPLIT": "0", "BIN_B200_PAIR": "1"}, {"BIN_B200_MSPLIT": "1", "BIN_B200_PAIR": "1"},
+            {"BIN_B200_MSPLIT": "0"}, {"BIN_B200_MSPLIT": "1"}]
     for cfg in cfgs:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, **cfg), capture_output=True,
                            text=True, timeout=600)
