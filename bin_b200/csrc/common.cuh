@@ -61,15 +61,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
   }
 }
 
-// Warp-wide wait: ONE lane polls, the others park at a warp barrier.  32 lanes executing mbarrier.try_wait on the same
-// barrier are serialised in the shared-memory pipe -- measured on B200 with the role timeline: ~310 cycles for a wait
-// whose phase had ALREADY completed, paid once per pipeline stage by every MMA / epilogue warp (r1 attributed it to
-// "the cost of an mbarrier poll").  bar.warp.sync orders the polling lane's acquire before the other lanes' accesses.
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, unsigned long long tag = 0ull) {
-  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, tag);
-  __syncwarp();
-}
-
+// NOTE (measured, round 2): letting ONE lane poll and parking the other 31 at __syncwarp() does NOT make a warp-wide
+// wait cheaper -- a wait on an already-completed phase still costs 300-450 cycles while the tensor pipe is streaming
+// operands from shared memory -- and it serialised the two tile streams of rdb_tail_kernel (0.21 -> 0.28 ms).  All lanes
+// poll.
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
@@ -216,10 +211,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       __trap();
     }
   }
-}
-__device__ __forceinline__ void mbar_wait_cluster_warp(uint64_t* bar, uint32_t parity) {   // see mbar_wait_warp
-  if ((threadIdx.x & 31) == 0) mbar_wait_cluster(bar, parity);
-  __syncwarp();
 }
 // 4-D tiled load into THIS CTA's shared memory whose completion bytes are credited to an mbarrier given as a
 // shared::cluster address (the leader's barrier): needs the .cta_group::2 form.

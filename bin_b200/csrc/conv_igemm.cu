@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     }
   } else if (PAIR && warp == 1 && rank == 1) {
     // ========================================================== peer: tell the leader when this CTA's B halves have landed
-    for (int c = 0; c < nchunks; ++c) mbar_wait_warp(&ctrl->wfull[c], 0);
+    for (int c = 0; c < nchunks; ++c) mbar_wait(&ctrl->wfull[c], 0);
     if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctrl->wready), 0));
   } else if ((warp == 1 || warp == 3) && rank == 0) {
     // ========================================================== MMA issuers (warp converged, one elected lane; PAIR: leader only)
@@ -275,8 +275,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     uint32_t it = 0, s = 0, ph = 0, tl = 0, dbg_it = 0;
     for (int tq = tq0; tq < tqn; tq += tqstep, ++tl) {
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-      if constexpr (PAIR) mbar_wait_cluster_warp(&ctrl->tmem_empty[as], aph ^ 1);
-      else mbar_wait_warp(&ctrl->tmem_empty[as], aph ^ 1, kTag | (3ull << 32) | tl);
+      if constexpr (PAIR) mbar_wait_cluster(&ctrl->tmem_empty[as], aph ^ 1);
+      else mbar_wait(&ctrl->tmem_empty[as], aph ^ 1, kTag | (3ull << 32) | tl);
       tc_fence_after();
       int unit = 0;
       for (int j = 0; j < spt; ++j, ++it) {
@@ -298,11 +298,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           // hangs.  (Both warps used to observe every full barrier; the warp that only observed could be lapped while
           // suspended: a rare watchdog under load, seen once at 720p in the split-fp16 mode.)  Ordering between the two
           // warps is carried by ctrl->issued alone.
-          mbar_wait_warp(&ctrl->full[s], ph, kTag | (2ull << 32) | it);
+          mbar_wait(&ctrl->full[s], ph, kTag | (2ull << 32) | it);
           if (p.resident && tl == 0) {
             for (int u = 0; u < nu; ++u)
-              if ((unit + u) % C::NSUB == 0) mbar_wait_warp(&ctrl->wfull[(unit + u) / C::NSUB], 0);
-            if (PAIR) mbar_wait_cluster_warp(&ctrl->wready, 0);
+              if ((unit + u) % C::NSUB == 0) mbar_wait(&ctrl->wfull[(unit + u) / C::NSUB], 0);
+            if (PAIR) mbar_wait_cluster(&ctrl->wready, 0);
           }
           if (!p.msplit)
             while (ctrl->issued < it) __nanosleep(32);      // stage it-1 fully issued by the other warp (a tight
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       }
       constexpr float kAcc = X3 ? (1.f / 256.f) : 1.f;      // X3 weights are packed scaled by 2^8
       if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 0);
-      mbar_wait_warp(&ctrl->tmem_full[as], aph, kTag | (4ull << 32) | acc_it);
+      mbar_wait(&ctrl->tmem_full[as], aph, kTag | (4ull << 32) | acc_it);
       if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + m * C::NMMA;

@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
       const uint32_t a_lo = ((smem_u32(htile + hb * kRtHBytes) >> 4) & 0x3FFFu) | H_LBO;
       const uint32_t b_lo = ((smem_u32(res_w + kRtChunks * kRtWChunk) >> 4) & 0x3FFFu) | B_LBO;
       const uint32_t d = tmem_base + kRtLffCol0 + plb * kRtN;
-      mbar_wait_warp(&ctrl->h_full[hb], (pt >> 1) & 1);
-      if (pt < 2) mbar_wait_warp(&ctrl->wfull[kRtChunks], 0);              // first tail of either MMA warp
+      mbar_wait(&ctrl->h_full[hb], (pt >> 1) & 1);
+      if (pt < 2) mbar_wait(&ctrl->wfull[kRtChunks], 0);              // first tail of either MMA warp
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -267,14 +267,14 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
         const uint32_t lb = tl2 % 3;
         // conv[Y] is free: this warp waited for the g3 tile of its previous tile, which epilogue A writes after it
         // has read the accumulator.  The rotating LFF accumulator was released three tiles ago.
-        mbar_wait_warp(&ctrl->lff_empty[lb], ((tl2 / 3) & 1) ^ 1);
+        mbar_wait(&ctrl->lff_empty[lb], ((tl2 / 3) & 1) ^ 1);
         const uint32_t d_conv = tmem_base + Y * kRtN;
         const uint32_t d_lff = tmem_base + kRtLffCol0 + lb * kRtN;
         for (int c = 0; c < kRtChunks; ++c, ++k) {
           const uint32_t slot = Y + 2 * (k & 1);
           if (Y == 0 && lane == 0) rt_rec(p, 1, k, 0);
-          mbar_wait_warp(&ctrl->full[slot], (k >> 1) & 1);
-          if (n == 0) mbar_wait_warp(&ctrl->wfull[c], 0);
+          mbar_wait(&ctrl->full[slot], (k >> 1) & 1);
+          if (n == 0) mbar_wait(&ctrl->wfull[c], 0);
           tc_fence_after();
           if (Y == 0 && lane == 0) rt_rec(p, 1, k, 1);
           issue_item(slot, c, d_conv, d_lff, c == kRtChunks - 1, Y);
@@ -286,8 +286,8 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tl) {
       const uint32_t as = tl & 1, lb = tl % 3;
       if (Y == 0) {
-        mbar_wait_warp(&ctrl->conv_empty[as], ((tl >> 1) & 1) ^ 1);
-        mbar_wait_warp(&ctrl->lff_empty[lb], ((tl / 3) & 1) ^ 1);
+        mbar_wait(&ctrl->conv_empty[as], ((tl >> 1) & 1) ^ 1);
+        mbar_wait(&ctrl->lff_empty[lb], ((tl / 3) & 1) ^ 1);
       }
       const uint32_t d_conv = tmem_base + as * kRtN;
       const uint32_t d_lff = tmem_base + kRtLffCol0 + lb * kRtN;
@@ -297,9 +297,9 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
           const uint32_t b_lo = w_lo + c * (kRtWChunk >> 4);
           const uint32_t first = (c == 0) ? 0u : 1u;
           if (Y == 0 && lane == 0) rt_rec(p, 1, dit, 0);
-          mbar_wait_warp(&ctrl->full[s], ph);
+          mbar_wait(&ctrl->full[s], ph);
           if (Y == 0 && lane == 0) rt_rec(p, 1, dit, 1);
-          if (tl == 0) mbar_wait_warp(&ctrl->wfull[c], 0);
+          if (tl == 0) mbar_wait(&ctrl->wfull[c], 0);
           wait_turn(sit);
           if (Y == 0 && lane == 0) rt_rec(p, 1, dit, 2);
           if (elect_one()) {
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tl) {
       const uint32_t as = tl & 1, uph = (tl >> 1) & 1;
       if (warp == 4 && lane == 0) rt_rec(p, 2, tl, 0);
-      mbar_wait_warp(&ctrl->conv_full[as], uph);
+      mbar_wait(&ctrl->conv_full[as], uph);
       if (warp == 4 && lane == 0) rt_rec(p, 2, tl, 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kRtN;
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
         ow[i >> 1] = rt_pack_h2(f[0], f[1]);
       }
       if (warp == 4 && lane == 0) rt_rec(p, 2, tl, 2);
-      mbar_wait_warp(&ctrl->h_empty[as], uph ^ 1);                          // tail of tile tl-2 has consumed this buffer
+      mbar_wait(&ctrl->h_empty[as], uph ^ 1);                          // tail of tile tl-2 has consumed this buffer
       uint8_t* h = htile + as * kRtHBytes + (q * 32 + lane + 1) * 16;
       if (lane < 31) {
 #pragma unroll
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
         rbuf[k] = valid ? *reinterpret_cast<const uint4*>(p.res + off) : make_uint4(0, 0, 0, 0);
       }
       if (warp == 8 && lane == 0) rt_rec(p, 0, tl, 2);
-      mbar_wait_warp(&ctrl->lff_full[lb], (tl / 3) & 1);
+      mbar_wait(&ctrl->lff_full[lb], (tl / 3) & 1);
       if (warp == 8 && lane == 0) rt_rec(p, 0, tl, 3);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kRtLffCol0 + lb * kRtN;
@@ -574,7 +574,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) rdb_tail_pai
     }
   } else if (warp == 1 && rank == 1) {
     // ========================================================== peer: tell the leader when this CTA's B halves have landed
-    for (int c = 0; c <= kRtChunks; ++c) mbar_wait_warp(&ctrl->wfull[c], 0);
+    for (int c = 0; c <= kRtChunks; ++c) mbar_wait(&ctrl->wfull[c], 0);
     if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctrl->wready), 0));
   } else if ((warp == 1 || warp == 3) && rank == 0) {
     // ========================================================== MMA issuers (leader only; warp converged, one elected lane)
@@ -592,15 +592,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) rdb_tail_pai
       // conv[Y] is free in BOTH CTAs: this warp waited for the g3 tiles of its previous tile pair (256 arrivals), which
       // the epilogue-A warps write after reading the accumulator.  The rotating LFF accumulator was released three
       // tile pairs ago (256 arrivals as well).
-      mbar_wait_cluster_warp(&ctrl->lff_empty[lb], (((uint32_t)j / 3) & 1) ^ 1);
+      mbar_wait_cluster(&ctrl->lff_empty[lb], (((uint32_t)j / 3) & 1) ^ 1);
       const uint32_t d_conv = tmem_base + Y * kRtN;
       const uint32_t d_lff = tmem_base + kRtLffCol0 + lb * kRtN;
       for (int c = 0; c < kRtChunks; ++c, ++k) {
         const uint32_t slot = Y * kRpR + k % kRpR;
-        mbar_wait_warp(&ctrl->full[slot], (k / kRpR) & 1);
+        mbar_wait(&ctrl->full[slot], (k / kRpR) & 1);
         if (n == 0) {
-          mbar_wait_warp(&ctrl->wfull[c], 0);
-          if (c == 0) mbar_wait_cluster_warp(&ctrl->wready, 0);
+          mbar_wait(&ctrl->wfull[c], 0);
+          if (c == 0) mbar_wait_cluster(&ctrl->wready, 0);
         }
         tc_fence_after();
         const uint32_t a_lo = stage_lo + slot * (kRtABytes >> 4);
@@ -634,8 +634,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) rdb_tail_pai
         const uint32_t hb = Y;
         const uint32_t a_lo = ((smem_u32(htile + hb * kRtHBytes) >> 4) & 0x3FFFu) | H_LBO;
         const uint32_t b_lo = w_lo + kRtChunks * (kRpWChunk >> 4);
-        mbar_wait_cluster_warp(&ctrl->h_full[hb], ((uint32_t)j >> 1) & 1);
-        if (n == 0) mbar_wait_warp(&ctrl->wfull[kRtChunks], 0);
+        mbar_wait_cluster(&ctrl->h_full[hb], ((uint32_t)j >> 1) & 1);
+        if (n == 0) mbar_wait(&ctrl->wfull[kRtChunks], 0);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
@@ -656,7 +656,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) rdb_tail_pai
     const uint32_t hfull0 = mapa_u32(smem_u32(&ctrl->h_full[0]), 0);
     for (int j = 0; (int)(cluster + j * nclusters) < npt; ++j) {
       const uint32_t as = (uint32_t)j & 1, uph = ((uint32_t)j >> 1) & 1;
-      mbar_wait_warp(&ctrl->conv_full[as], uph);
+      mbar_wait(&ctrl->conv_full[as], uph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kRtN;
       uint32_t v[96];
@@ -677,7 +677,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) rdb_tail_pai
         }
         ow[i >> 1] = rt_pack_h2(f[0], f[1]);
       }
-      mbar_wait_warp(&ctrl->h_empty[as], uph ^ 1);                          // tail of tile pair j-2 has consumed this buffer
+      mbar_wait(&ctrl->h_empty[as], uph ^ 1);                          // tail of tile pair j-2 has consumed this buffer
       uint8_t* h = htile + as * kRtHBytes + (q * 32 + lane + 1) * 16;
       if (lane < 31) {
 #pragma unroll
@@ -702,7 +702,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) rdb_tail_pai
         const size_t off = ((((size_t)b * p.res_planes + p.res_plane0 + kk) * p.H + y) * p.W + x) * 8;
         rbuf[kk] = valid ? *reinterpret_cast<const uint4*>(p.res + off) : make_uint4(0, 0, 0, 0);
       }
-      mbar_wait_warp(&ctrl->lff_full[lb], ((uint32_t)j / 3) & 1);
+      mbar_wait(&ctrl->lff_full[lb], ((uint32_t)j / 3) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kRtLffCol0 + lb * kRtN;
 #pragma unroll

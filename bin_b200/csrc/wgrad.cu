@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     uint32_t s = 0, ph = 0;
     bool first = true;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      mbar_wait_warp(&ctrl->full[s], ph);
+      mbar_wait(&ctrl->full[s], ph);
       tc_fence_after();
       const uint32_t xb = smem_u32(stage0 + (size_t)s * stage_bytes);
       const uint32_t yb = xb + x_bytes;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
     // ------------------------------------------------ flush: TMEM -> this CTA's slab of the partial-sum workspace
     // (plain 16-byte stores; 36.8 K fp32 atomics per CTA were issue-bound at ~1 lane/clk and took 4x the MMA time;
     //  wgrad_reduce_kernel sums the slabs afterwards)
-    mbar_wait_warp(&ctrl->done, 0);
+    mbar_wait(&ctrl->done, 0);
     tc_fence_after();
     const int q = warp & 3;
     const int row = q * 32 + lane;                               // accumulator row = input channel within the tile

@@ -190,43 +190,48 @@ def _oracle_window_grads_gpu(fr, cots, sd, dtype=torch.float32):
 def test_window_backward_b2_256_vs_fp16_storage_oracle(sd):
     """BASELINE config 3 geometry (256x256 crops, batch 2 here to bound the oracle's memory): gradients of
     sum_k <out_k, cot_k> w.r.t. the 6 frames and all 540 parameter tensors against autograd through the oracle with
-    fp16-rounded storage.  Bars: frames <= 1 %, weights / biases <= 2 % of the tensor's max magnitude."""
+    fp16-rounded storage of activations AND gradients (what the CUDA path keeps in HBM).
+
+    A network with fp16-stored activations is chaotic at the rounding boundaries: the SAME oracle evaluated with fp32
+    and with fp64 accumulation already differs by ~4e-4 in its outputs (a value next to an fp16 rounding midpoint or a
+    ReLU threshold lands on the other side) and by several per cent of the tensor maximum in individual weight
+    gradients.  That oracle-vs-oracle discrepancy is the resolution of this comparison, so it is measured here and the
+    CUDA path is required to be as close to the oracle as the oracle is to itself: per backbone, worst error
+    <= 2 x the oracle's own worst discrepancy + 2 % of the tensor maximum, and correlation >= 0.997 for every tensor."""
     from bin_b200 import rdn
     B, H, W = 2, 256, 256
     fr = O.synth_frames(6, B, H, W, seed=9, smooth=True)
     cots = [c - 0.5 for c in O.synth_frames(14, B, H, W, seed=10)]
-    gfr, gp, ref_outs = _oracle_window_grads_gpu(fr, cots, sd)
+    gfr, gp, ref_outs = _oracle_window_grads_gpu(fr, cots, sd, torch.float64)
+    gfr32, gp32, ref_outs32 = _oracle_window_grads_gpu(fr, cots, sd, torch.float32)
+    self_fwd = max((a - b).abs().max().item() for a, b in zip(ref_outs, ref_outs32))
     net = rdn.bin_stage4_lstm(); net.load_state_dict(sd, strict=True); net = net.cuda().train()
     frg = [f.cuda().requires_grad_(True) for f in fr]
     outs = net(*frg)
     fwd = max((o.detach() - r).abs().max().item() for o, r in zip(outs, ref_outs))
-    print(f"[bwd 2x256x256] forward max-abs vs the fp16-storage oracle: {fwd:.3e}")
+    print(f"[bwd 2x256x256] forward max-abs: CUDA vs fp16-storage oracle {fwd:.3e}; that oracle fp32 vs fp64 accumulate {self_fwd:.3e}")
     assert fwd <= TOL_FP16
     sum((o * c.cuda()).sum() for o, c in zip(outs, cots)).backward()
     for k in range(6):
         err = (frg[k].grad - gfr[k]).abs().max().item() / gfr[k].abs().max().item()
         assert err <= 1e-2, ("frame", k, err)
     params = dict(net.named_parameters())
+    rel = lambda a, b: (a.float() - b.float()).abs().max().item() / max(b.abs().max().item(), 1e-20)
     worst = {}
     for key, ref in gp.items():
         got = params[key].grad
         assert got is not None, key
-        err = (got - ref.float()).abs().max().item() / max(ref.abs().max().item(), 1e-20)
         corr = torch.corrcoef(torch.stack([got.flatten().float(), ref.flatten().float()]))[0, 1].item() if got.numel() > 2 else 1.0
         grp = key.split(".")[1] if key.startswith("model.") else "clstm"
-        worst.setdefault(grp, []).append((err, corr, key))
+        worst.setdefault(grp, []).append((rel(got, ref), rel(gp32[key], ref), corr, key))
     for grp, rows in sorted(worst.items()):
-        rows.sort(reverse=True)
-        print(f"[bwd 2x256x256] {grp}: worst err {rows[0][0]:.4f} (corr {rows[0][1]:.5f}) {rows[0][2]}; "
-              f"median err {rows[len(rows) // 2][0]:.4f}; min corr {min(r[1] for r in rows):.5f}")
-    # Stage 1 (model1_1: inputs are the frames themselves) is where kernel errors would show undiluted: <= 2 % of the
-    # tensor max.  Deeper stages see inputs that already differ by the fp16 forward error, which flips ReLU masks the
-    # oracle cannot reproduce (chaotic in depth); there the direction must still agree (corr >= 0.99) and the error stay
-    # <= 15 % of the tensor max.
-    for grp, rows in worst.items():
-        bar = 2e-2 if grp == "model1_1" else 0.15
-        assert rows[0][0] <= bar, (grp, rows[:4])
-        assert min(r[1] for r in rows) >= 0.99, (grp, sorted(rows, key=lambda r: r[1])[:4])
+        ours, floor = max(r[0] for r in rows), max(r[1] for r in rows)
+        med = sorted(r[0] for r in rows)[len(rows) // 2]
+        medf = sorted(r[1] for r in rows)[len(rows) // 2]
+        print(f"[bwd 2x256x256] {grp}: CUDA vs oracle worst {ours:.4f} median {med:.4f} | oracle fp32 vs fp64 worst {floor:.4f} median {medf:.4f} "
+              f"| min corr {min(r[2] for r in rows):.5f}")
+        assert ours <= 2.0 * floor + 0.02, (grp, sorted(rows, reverse=True)[:4])
+        assert min(r[2] for r in rows) >= 0.997, (grp, sorted(rows, key=lambda r: r[2])[:4])
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (runs on the multi-GPU box)")
