@@ -27,6 +27,7 @@ static Options read_options() {
   o.tail_streams = !((e = env("BIN_B200_TAIL_STREAMS")) && *e == '0');
   o.pair = (e = env("BIN_B200_PAIR")) && *e == '1';     // CTA-pair kernels: opt-in until verified on hardware
   o.msplit = (e = env("BIN_B200_MSPLIT")) && *e == '1';
+  o.zigzag = (e = env("BIN_B200_ZIGZAG")) && *e == '1';
   o.stage_mmas = (e = env("BIN_B200_STAGE_MMAS")) ? atoi(e) : 12;
   if (o.stage_mmas < 1) o.stage_mmas = 12;
   o.band_budget = (e = env("BIN_B200_BAND_BUDGET_KB")) ? (size_t)atoll(e) << 10 : (~(size_t)0 >> 1);
@@ -85,7 +86,7 @@ int launch_blur_average_u8(const uint8_t* frames, int T, size_t frame_bytes, int
                            int nwin, uint8_t* out, cudaStream_t s);
 int launch_rdb_tail(const bin_act_t& x, int x_plane0, const bin_act_t& g, int g_plane0, const void* w_conv,
                     const float* b_conv, const void* w_lff, const float* b_lff, const bin_act_t& out, int out_plane0,
-                    int b_begin, int b_count, int y_begin, int y_count, cudaStream_t s);
+                    int b_begin, int b_count, int y_begin, int y_count, cudaStream_t s, bool reverse = false);
 int launch_tensor2img_u8(const float* x, int Hs, int Ws, int top, int left, int h, int w, uint8_t* out, cudaStream_t s);
 int launch_u8_to_frame(const uint8_t* img, int h, int w, int pl, int pr, int pt, int pb, float* out, cudaStream_t s);
 int launch_convlstm_bwd(const float* x, const float* c_prev, const float* h_prev, const float* w, const float* b,
@@ -269,7 +270,10 @@ static int run_rdb(const void* blob, const BackboneLayout& L, int i, const bin_a
       const int ext = kCgrow - 1 - c;             // rows still needed by the convs downstream in this band
       const int lo = bd.y0 - ext < 0 ? 0 : bd.y0 - ext, hi = bd.y1 + ext > h ? h : bd.y1 + ext;
       a.b_begin = bd.b0; a.b_count = bd.nb; a.y_begin = lo; a.y_count = hi - lo;
-      BIN_TRY(launch_conv(a, s));
+      // zigzag: conv0 forward, conv1 backward, conv2 forward, tail backward -- every launch starts on the tiles its
+      // predecessor touched last, which are the ones still in the 126 MB L2 (the tail ends at tile 0, where the next
+      // RDB's conv0 starts)
+      BIN_TRY(launch_conv(a, s, options().zigzag && (c & 1)));
     }
     if (fuse) {
       const ConvSpec& c3 = L.conv[base + kCgrow - 1];
@@ -277,7 +281,7 @@ static int run_rdb(const void* blob, const BackboneLayout& L, int i, const bin_a
       BIN_TRY(launch_rdb_tail(xin, x_plane0, g, g_plane0, (const uint8_t*)blob + c3.w_off,
                               (const float*)((const uint8_t*)blob + c3.b_off), (const uint8_t*)blob + lf.w_off,
                               (const float*)((const uint8_t*)blob + lf.b_off), out, out_plane0, bd.b0, bd.nb, bd.y0,
-                              bd.y1 - bd.y0, s));
+                              bd.y1 - bd.y0, s, options().zigzag));
       continue;
     }
     bin_conv_args_t a = conv_args(blob, L.conv[base + kCgrow], x3);

@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   auto tile_at = [&](int tq, bool& live) {
     int t = PAIR ? 2 * tq + (int)rank : tq;
     live = t < p.ntiles;
-    return live ? t : p.ntiles - 1;
+    if (!live) t = p.ntiles - 1;
+    return p.reverse ? p.ntiles - 1 - t : t;
   };
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
@@ -660,7 +661,7 @@ int make_p8_tmap_box(CUtensorMap* m, const bin_act_t& t, int box_px, int box_row
 }
 
 template <int NT, int KS, int EPI, bool SX, bool X3>
-static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
+static int launch_inst(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
   using C = ConvCfg<NT, KS, SX>;
   ConvParams p;
   memset(&p, 0, sizeof(p));
@@ -717,6 +718,7 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
   p.fr = a.fr;
   p.debug = options().debug;
   p.msplit = options().msplit ? 1 : 0;
+  p.reverse = (reverse && EPI == BIN_EPI_P8) ? 1 : 0;     // (the FINAL epilogue prefetches tile + gridDim.x: forward only)
 #ifdef BIN_B200_TOOLS
   if (p.debug & 8) {
     if (!g_dbg) { BIN_CUDA_OK(cudaMalloc(&g_dbg, 3 * 4096 * sizeof(long long))); }
@@ -765,7 +767,7 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s) {
 }
 
 template <bool X3>
-static int launch_conv_t(const bin_conv_args_t& a, cudaStream_t s) {
+static int launch_conv_t(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
   constexpr int f = X3 ? 2 : 1;      // X3 tensors hold hi+lo: twice the planes of their logical channel count
   if (a.in0_planes % kKPL || a.in1_planes % kKPL || a.in0_planes <= 0)
     return fail(BIN_ERR_ARG, "input plane counts must be positive multiples of 4 (32 channels)");
@@ -781,28 +783,28 @@ static int launch_conv_t(const bin_conv_args_t& a, cudaStream_t s) {
     if (a.res.ptr && (a.res.H != a.in0.H || a.res.W != a.in0.W || a.res.B != a.in0.B ||
                       f * (a.res_plane0 + nstore) > a.res.planes + (X3 ? 4 : 0)))
       return fail(BIN_ERR_ARG, "residual tensor geometry mismatch");
-    if (a.ksize == 3 && a.cout_pad == 32 && a.variant == 0) return launch_inst<32, 3, BIN_EPI_P8, true, X3>(a, s);
-    if (a.ksize == 3 && a.cout_pad == 32 && a.variant == 1 && !X3) return launch_inst<32, 3, BIN_EPI_P8, false, false>(a, s);
-    if (a.ksize == 3 && a.cout_pad % 96 == 0) return launch_inst<96, 3, BIN_EPI_P8, false, X3>(a, s);
-    if (a.ksize == 5 && a.cout_pad == 96) return launch_inst<96, 5, BIN_EPI_P8, false, X3>(a, s);
-    if (a.ksize == 1 && a.cout_pad % 96 == 0) return launch_inst<96, 1, BIN_EPI_P8, false, X3>(a, s);
+    if (a.ksize == 3 && a.cout_pad == 32 && a.variant == 0) return launch_inst<32, 3, BIN_EPI_P8, true, X3>(a, s, reverse);
+    if (a.ksize == 3 && a.cout_pad == 32 && a.variant == 1 && !X3) return launch_inst<32, 3, BIN_EPI_P8, false, false>(a, s, reverse);
+    if (a.ksize == 3 && a.cout_pad % 96 == 0) return launch_inst<96, 3, BIN_EPI_P8, false, X3>(a, s, reverse);
+    if (a.ksize == 5 && a.cout_pad == 96) return launch_inst<96, 5, BIN_EPI_P8, false, X3>(a, s, reverse);
+    if (a.ksize == 1 && a.cout_pad % 96 == 0) return launch_inst<96, 1, BIN_EPI_P8, false, X3>(a, s, reverse);
   } else if (a.epilogue == BIN_EPI_PIXSHUF) {
     if (a.out.H != 2 * a.in0.H || a.out.W != 2 * a.in0.W || a.out.B != a.in0.B ||
         f * (a.out_plane0 + a.cout_pad / 32) > a.out.planes)
       return fail(BIN_ERR_ARG, "pixel-shuffle output geometry mismatch");
-    if (a.ksize == 3 && a.cout_pad == 256) return launch_inst<128, 3, BIN_EPI_PIXSHUF, false, X3>(a, s);
+    if (a.ksize == 3 && a.cout_pad == 256) return launch_inst<128, 3, BIN_EPI_PIXSHUF, false, X3>(a, s, reverse);
   } else if (a.epilogue == BIN_EPI_FINAL) {
     if (a.fr.ncalls < 1 || a.fr.ncalls > BIN_MAX_CALLS || a.fr.nframes < 1 || a.fr.nframes > BIN_MAX_FRAMES ||
         a.fr.ncalls * a.fr.Bc != a.in0.B)
       return fail(BIN_ERR_ARG, "frame table does not match the batch");
-    if (a.ksize == 3 && a.cout_pad == 16 && a.variant == 0) return launch_inst<16, 3, BIN_EPI_FINAL, true, X3>(a, s);
-    if (a.ksize == 3 && a.cout_pad == 16 && a.variant == 1 && !X3) return launch_inst<16, 3, BIN_EPI_FINAL, false, false>(a, s);
+    if (a.ksize == 3 && a.cout_pad == 16 && a.variant == 0) return launch_inst<16, 3, BIN_EPI_FINAL, true, X3>(a, s, reverse);
+    if (a.ksize == 3 && a.cout_pad == 16 && a.variant == 1 && !X3) return launch_inst<16, 3, BIN_EPI_FINAL, false, false>(a, s, reverse);
   }
   return fail(BIN_ERR_UNSUPPORTED, "no kernel instantiation for this conv (ksize/cout_pad/epilogue/precision)");
 }
 
-int launch_conv(const bin_conv_args_t& a, cudaStream_t s) {
-  return a.x3 ? launch_conv_t<true>(a, s) : launch_conv_t<false>(a, s);
+int launch_conv(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
+  return a.x3 ? launch_conv_t<true>(a, s, reverse) : launch_conv_t<false>(a, s, reverse);
 }
 
 }  // namespace binb

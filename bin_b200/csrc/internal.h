@@ -50,6 +50,7 @@ struct Options {
   bool tail_streams;         // BIN_B200_TAIL_STREAMS=0 selects the hand-off variant of rdb_tail_kernel
   bool pair;                 // BIN_B200_PAIR=1 selects the CTA-pair (cta_group::2) kernels (measured slower: opt-in)
   bool msplit;               // BIN_B200_MSPLIT: conv MMA warps split the tile's two accumulators instead of alternating stages
+  bool zigzag;               // BIN_B200_ZIGZAG: consecutive RDB launches walk the tiles in opposite directions (L2 reuse)
   int stage_mmas;            // BIN_B200_STAGE_MMAS: target MMAs per pipeline stage of the conv kernel (default 12)
   size_t band_budget;        // BIN_B200_BAND_BUDGET_KB (L2 band walker; default: one band)
 };
@@ -76,7 +77,7 @@ struct alignas(64) ConvParams {
   int H, W, Btot;                      // conv resolution
   int b0, y0, ny;                      // batch / row sub-range processed by this launch
   int tiles_x, tiles_y, ntiles, nh;    // nh = cout_pad / NT
-  int relu, resident, nstages, cps, debug, msplit;
+  int relu, resident, nstages, cps, debug, msplit, reverse;
   __half* out; int out_planes, out_plane0, store_planes;
   const __half* res; int res_planes, res_plane0;
   bin_frames_t fr;
@@ -84,7 +85,7 @@ struct alignas(64) ConvParams {
 };
 extern long long* g_dbg;
 
-int launch_conv(const bin_conv_args_t& a, cudaStream_t s);
+int launch_conv(const bin_conv_args_t& a, cudaStream_t s, bool reverse = false);   // reverse: walk the tiles last-to-first
 
 // up to 3 independent ConvLSTM cells in one launch (aux_kernels.cu)
 struct LstmCells {

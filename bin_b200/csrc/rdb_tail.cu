@@ -62,6 +62,7 @@ struct alignas(64) RdbTailParams {
   int tiles_x, tiles_y, ntiles;
   __half* out; int out_planes, out_plane0;
   const __half* res; int res_planes, res_plane0;
+  int reverse;                          // walk the tiles last-to-first (zigzag L2 reuse across launches)
   int debug; long long* dbg;            // BIN_B200_DEBUG=8: block 0 records clock64 at role milestones (tools only)
 };
 // timeline layout (bin_debug_timeline): [role][iter][4]; role 0 = producer (k 0,1 per stage) and epilogue B (k 2,3 per tile),
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
     uint32_t k = 0;
     for (uint32_t tl = STREAMS ? Y : 0; (int)(blockIdx.x + tl * gridDim.x) < p.ntiles; tl += STREAMS ? 2 : 1) {
       int t = blockIdx.x + tl * gridDim.x;
+      if (p.reverse) t = p.ntiles - 1 - t;
       const int txi = t % p.tiles_x; t /= p.tiles_x;
       const int tyi = t % p.tiles_y;
       const int b = p.b0 + t / p.tiles_y;
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
     const int q = warp & 3;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tl) {
-      int t = tile;
+      int t = p.reverse ? p.ntiles - 1 - tile : tile;
       const int txi = t % p.tiles_x; t /= p.tiles_x;
       const int tyi = t % p.tiles_y;
       const int b = p.b0 + t / p.tiles_y;
@@ -534,6 +536,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) rdb_tail_pai
     int t = 2 * q + (int)rank;
     live = t < p.ntiles;
     if (!live) t = p.ntiles - 1;
+    if (p.reverse) t = p.ntiles - 1 - t;
     txi = t % p.tiles_x; t /= p.tiles_x;
     tyi = t % p.tiles_y;
     b = p.b0 + t / p.tiles_y;
@@ -753,7 +756,7 @@ int make_p8_tmap(CUtensorMap* m, const bin_act_t& t, int box_rows);   // conv_ig
 
 int launch_rdb_tail(const bin_act_t& x, int x_plane0, const bin_act_t& g, int g_plane0, const void* w_conv,
                     const float* b_conv, const void* w_lff, const float* b_lff, const bin_act_t& out, int out_plane0,
-                    int b_begin, int b_count, int y_begin, int y_count, cudaStream_t s) {
+                    int b_begin, int b_count, int y_begin, int y_count, cudaStream_t s, bool reverse) {
   const int H = x.H, W = x.W, B = x.B;
   if (g.H != H || g.W != W || g.B != B || out.H != H || out.W != W || out.B != B)
     return fail(BIN_ERR_ARG, "rdb_tail: tensor geometry mismatch");
@@ -777,6 +780,7 @@ int launch_rdb_tail(const bin_act_t& x, int x_plane0, const bin_act_t& g, int g_
   p.ntiles = nb * p.tiles_x * p.tiles_y;
   p.out = reinterpret_cast<__half*>(out.ptr); p.out_planes = out.planes; p.out_plane0 = out_plane0;
   p.res = reinterpret_cast<const __half*>(x.ptr); p.res_planes = x.planes; p.res_plane0 = x_plane0;
+  p.reverse = reverse ? 1 : 0;
   const bool streams = options().tail_streams;
   p.debug = options().debug;
 #ifdef BIN_B200_TOOLS
