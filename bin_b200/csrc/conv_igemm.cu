@@ -67,7 +67,7 @@ struct Ctrl {
   uint64_t tmem_empty[2];
   uint64_t wready;            // PAIR: the peer's resident weight halves have landed (leader's copy is used)
   uint32_t tmem_base;
-  volatile uint32_t issued;   // number of pipeline stages whose MMAs have been issued (MMA warp hand-off)
+  volatile uint32_t issued[2];   // per accumulator (QUAD) / [0] only: number of pipeline stages whose MMAs have been issued (hand-off)
 };
 static_assert(sizeof(Ctrl) <= 1024, "ctrl block");
 
@@ -133,10 +133,16 @@ __device__ __forceinline__ void split_store(__half* base_hi, __half* base_lo, co
 // of this kernel), and half the resident-weight footprint (two more ring slots for the 160-channel conv).
 // Barriers as in rdb_tail_pair_kernel: `full` in the leader (2 x bytes, both CTAs' TMA credit it), `empty` / `tmem_full`
 // by multicast commit into both CTAs, `tmem_empty` in the leader counting the epilogue threads of both CTAs.
-template <int NT, int KS, int EPI, bool SX, bool X3, bool PAIR = false>
-__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+// QUAD (448 threads; x-stacked fp16 convs, single CTA): FOUR MMA warps -- accumulator m of the tile is fed by the two warps
+// (m, stage parity 0 / 1), which alternate stages and hand over through issued[m] exactly as the two warps of the default
+// scheme do.  The role timelines show a single issuing warp sustaining one MMA per ~82 cycles while two warps issuing
+// CONCURRENTLY reach the isolated rate (57); with four warps two are always issuing (one per accumulator) while the other
+// two wait on their next barrier.  The MMA order per accumulator is unchanged -> bit-identical results.
+template <int NT, int KS, int EPI, bool SX, bool X3, bool PAIR = false, bool QUAD = false>
+__global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using C = ConvCfg<NT, KS, SX>;
   static_assert(!PAIR || (SX && !X3 && EPI == BIN_EPI_P8), "the CTA-pair form exists for the x-stacked fp16 convs");
+  static_assert(!QUAD || (SX && !X3 && EPI == BIN_EPI_P8 && !PAIR), "the four-MMA-warp form exists for the x-stacked fp16 convs");
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   // tile sequence of this CTA: single CTA -> tiles blockIdx.x, +gridDim.x, ...; pair -> tile pair q = cluster, +nclusters, ...
   // with tile 2q + rank (the peer of an odd tail re-runs the last tile with its stores suppressed)
@@ -176,15 +182,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     if (p.nch1 > 0) tma_prefetch_desc(&p.tmap1);
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&ctrl->full[i], 1);
-      mbar_init(&ctrl->empty[i], p.msplit ? 2 : 1);        // M-split: both MMA warps consume every stage
+      mbar_init(&ctrl->empty[i], (QUAD || p.msplit) ? 2 : 1);   // M-split / QUAD: two MMA warps consume every stage
     }
     for (int i = 0; i < kMaxResidentChunks; ++i) mbar_init(&ctrl->wfull[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&ctrl->tmem_full[i], 2);
+      mbar_init(&ctrl->tmem_full[i], QUAD ? 4 : 2);        // one tcgen05.commit per MMA warp
       mbar_init(&ctrl->tmem_empty[i], PAIR ? 512 : 256);   // epilogue threads (of both CTAs)
     }
     mbar_init(&ctrl->wready, 1);
-    ctrl->issued = 0;
+    ctrl->issued[0] = ctrl->issued[1] = 0;
     fence_barrier_init();
   }
   const bool bias_in_smem = NT * p.nh <= 256;                  // else (wide data-gradient launches) read it from global
@@ -266,9 +272,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     // ========================================================== peer: tell the leader when this CTA's B halves have landed
     for (int c = 0; c < nchunks; ++c) mbar_wait(&ctrl->wfull[c], 0);
     if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctrl->wready), 0));
-  } else if ((warp == 1 || warp == 3) && rank == 0) {
+  } else if ((warp == 1 || warp == 3 || (QUAD && warp >= 12)) && rank == 0) {
     // ========================================================== MMA issuers (warp converged, one elected lane; PAIR: leader only)
-    const uint32_t Y = warp >> 1;
+    const uint32_t Y = QUAD ? ((warp == 1 || warp == 12) ? 0u : 1u) : (uint32_t)(warp >> 1);   // stage parity this warp issues
+    const uint32_t mq = (QUAD && warp >= 12) ? 1u : 0u;                                        // QUAD: its accumulator
     constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 256 : 128, C::NMMA);
     constexpr uint32_t D_HI = (128u >> 4) | (1u << 14);            // SBO=128 B, descriptor version 1
     constexpr uint32_t A_LBO = ((uint32_t)C::A_PLANE >> 4) << 16;
@@ -290,8 +297,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         //    128 Y .. 128 Y + 127).  The two accumulators are independent, so nothing orders the warps against each other
         //    (no hand-off, no shared counter); a stage is recycled when both have committed (empty count 2), so neither
         //    waiter can be lapped.  The per-accumulator MMA order is unchanged -> bit-identical results.
-        const bool mine = p.msplit ? true : (it & 1u) == Y;
-        if (mine && Y == 0 && lane == 0) dbg_rec(p, 1, dbg_it, 0);
+        const bool mine = (!QUAD && p.msplit) ? true : (it & 1u) == Y;
+        if (mine && warp == 1 && lane == 0) dbg_rec(p, 1, dbg_it, 0);
         if (mine) {
           // Each MMA warp waits ONLY on the stages it issues (S is even, so stage parity = warp): a parity-tracked
           // mbarrier must never be waited on by a thread that can fall a whole phase behind -- mbarrier.try_wait may
@@ -305,10 +312,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
               if ((unit + u) % C::NSUB == 0) mbar_wait(&ctrl->wfull[(unit + u) / C::NSUB], 0);
             if (PAIR) mbar_wait_cluster(&ctrl->wready, 0);
           }
-          if (!p.msplit)
-            while (ctrl->issued < it) __nanosleep(32);      // stage it-1 fully issued by the other warp (a tight
+          if (QUAD || !p.msplit)
+            while (ctrl->issued[mq] < it) __nanosleep(32);  // stage it-1 fully issued by the other warp (a tight
                                                             // shared-memory spin would compete with the MMA operand fetch)
-          if (Y == 0 && lane == 0) dbg_rec(p, 1, dbg_it, 1);
+          if (warp == 1 && lane == 0) dbg_rec(p, 1, dbg_it, 1);
           tc_fence_after();
           const uint32_t st_base = smem_u32(stage0 + (size_t)s * stage_bytes);
           for (int u = 0; u < nu; ++u) {
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             if (elect_one()) {
 #pragma unroll
               for (int m = 0; m < kMT; ++m) {
-                if (p.msplit && (uint32_t)m != Y) continue;
+                if (QUAD ? (uint32_t)m != mq : (p.msplit && (uint32_t)m != Y)) continue;
                 const uint32_t d = tmem_base + as * C::ACC_COLS + m * C::NMMA;
 #pragma unroll
                 for (int tp = 0; tp < C::TAPS_S; ++tp) {
@@ -348,8 +355,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           }
           tc_fence_before();                               // order this warp's tcgen05.mma before the flag (the
           __syncwarp();                                    // other warp pairs it with tc_fence_after above)
-          if (lane == 0 && !p.msplit) ctrl->issued = it + 1;   // hand the tensor pipe to the other MMA warp
-          if (Y == 0 && lane == 0) dbg_rec(p, 1, dbg_it, 2);
+          if (lane == 0 && (QUAD || !p.msplit)) ctrl->issued[mq] = it + 1;   // hand over to the warp of the other stage parity
+          if (warp == 1 && lane == 0) dbg_rec(p, 1, dbg_it, 2);
           ++dbg_it;
         }
         unit += nu;
@@ -361,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       }
       __syncwarp();
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     // ========================================================== epilogue
     const int q = warp & 3;
     const int m = (warp - 4) >> 2;                      // which 128-row accumulator of the tile
@@ -743,6 +750,18 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       BIN_CUDA_OK(cudaLaunchKernelEx(&cfg, kp, p));
+      return BIN_OK;
+    }
+  }
+  if constexpr (kPairable) {
+    if (options().quad) {
+      auto kq = conv_igemm_kernel<NT, KS, EPI, SX, X3, false, true>;
+      static std::atomic<unsigned long long> quad_opted{0};   // per device
+      BIN_TRY(ensure_dynamic_smem(kq, kSmemMax, quad_opted));
+      const int gq = p.ntiles < num_sms() ? p.ntiles : num_sms();
+      if (gq < 1) return BIN_OK;
+      kq<<<gq, kThreads + 64, smem_bytes, s>>>(p);
+      BIN_CUDA_OK(cudaGetLastError());
       return BIN_OK;
     }
   }

@@ -296,7 +296,8 @@ def test_fp32_mode_window_vs_oracle(net32, sd):
 def test_cta_pair_kernels_bit_identical_to_single_cta():
     """The cta_group::2 kernels (rdb_tail_pair_kernel, conv_igemm_kernel<...,PAIR>) and the M-split MMA-warp scheme of the
     conv kernel keep the per-accumulator MMA order of the default kernels: a whole window must hash identically under
-    every combination of BIN_B200_PAIR / BIN_B200_MSPLIT / BIN_B200_ZIGZAG (reversed tile order of alternate launches); the
+    every combination of BIN_B200_PAIR / BIN_B200_MSPLIT / BIN_B200_QUAD (four MMA warps) / BIN_B200_ZIGZAG (reversed tile
+    order of alternate launches); the
     library reads the switches once per process, hence children.  Shapes: odd tile counts (dummy peer tile), many tiles per cluster."""
     import subprocess
     import sys
@@ -314,6 +315,7 @@ def test_cta_pair_kernels_bit_identical_to_single_cta():
     got = {}
     for tag, env in (("single", {"BIN_B200_PAIR": "0", "BIN_B200_MSPLIT": "0"}), ("pair", {"BIN_B200_PAIR": "1", "BIN_B200_MSPLIT": "0"}),
                      ("msplit", {"BIN_B200_PAIR": "0", "BIN_B200_MSPLIT": "1"}), ("pair+msplit", {"BIN_B200_PAIR": "1", "BIN_B200_MSPLIT": "1"}),
+                     ("quad", {"BIN_B200_QUAD": "1"}), ("quad+zigzag", {"BIN_B200_QUAD": "1", "BIN_B200_ZIGZAG": "1"}),
                      ("zigzag", {"BIN_B200_ZIGZAG": "1"}), ("pair+zigzag", {"BIN_B200_PAIR": "1", "BIN_B200_ZIGZAG": "1"})):
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, (tag, r.stderr[-2000:])

@@ -29,7 +29,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         return e0.elapsed_time(e1) / reps
     x = torch.randn(B, 12, h, w, 8, device=dev).half()
     g = torch.randn(B, 16, h, w, 8, device=dev).half()
-    res = {"cfg": {k: os.environ.get(k, "") for k in ("BIN_B200_MSPLIT", "BIN_B200_STAGE_MMAS", "BIN_B200_PAIR")}}
+    res = {"cfg": {k: os.environ.get(k, "") for k in ("BIN_B200_QUAD", "BIN_B200_MSPLIT", "BIN_B200_STAGE_MMAS", "BIN_B200_PAIR")}}
     tot, fl = 0.0, 0.0
     for c in range(3):
         cin = 96 + 32 * c
@@ -50,9 +50,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         res["window_ms"] = round(t(lambda: net(*fr), reps=10), 3)
     print(json.dumps(res))
 else:
-    cfgs = [{"BIN_B200_MSPLIT": "0"}, {"BIN_B200_MSPLIT": "1"}, {"BIN_B200_MSPLIT": "1", "BIN_B200_STAGE_MMAS": "24"},
-            {"BIN_B200_MSPLIT": "0", "BIN_B200_PAIR": "1"}, {"BIN_B200_MSPLIT": "1", "BIN_B200_PAIR": "1"},
-            {"BIN_B200_MSPLIT": "0"}, {"BIN_B200_MSPLIT": "1"}]
+    cfgs = [{}, {"BIN_B200_QUAD": "1"}, {"BIN_B200_MSPLIT": "1"}, {"BIN_B200_PAIR": "1"}, {}, {"BIN_B200_QUAD": "1"},
+            {"BIN_B200_QUAD": "1", "BIN_B200_STAGE_MMAS": "24"}]
     for cfg in cfgs:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, **cfg), capture_output=True,
                            text=True, timeout=600)

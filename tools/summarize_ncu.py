@@ -69,7 +69,8 @@ def full(rep, title, note, extra=()):
     rows = list(csv.reader(out.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ix = {h: i for i, h in enumerate(hdr)}
-    with open(os.path.join(P, f"{tag}_{rep.replace('.ncu-rep','')}.md"), "w") as f:
+    base = re.sub(r"^r\d+[a-z]\d*_", "", rep.replace(".ncu-rep", ""))          # r02f_prof_tail -> prof_tail
+    with open(os.path.join(P, f"{tag}_{base}.md"), "w") as f:
         f.write(f"# {tag}: {title}\n\n{note}\n\n| metric | " + " | ".join(short(d[ix['Kernel Name']]) for d in data) + " |\n")
         f.write("|---|" + "---|" * len(data) + "\n")
         for m, label in list(WANT) + list(extra):
@@ -94,20 +95,23 @@ if tag == "r01":
          "Algorithmic FLOPs per launch: 2*5*230400*(192*32*9 + 224*96).")
 
 if tag == "r02":
-    launches("r02b_launches_window.csv", "r02_launches_window.md",
+    launches("r02f_launches_window.csv", "r02_launches_window.md",
              "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 227 -c 223 --csv python tools/run_window.py 2` "
              "(BIN_B200_GRAPH=0; skip = 4 batched weight-pack launches + the 223 launches of window 0; CTA-pair kernels on).")
     FP = [("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe % of peak"),
           ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots active %"),
           ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts")]
-    full("r02a2_prof_k345.ncu-rep", "ncu --set full: the memory-/FP32-bound kernels of one window: K3 pack_frames, K5 convlstm, (K4 = final conv, see r02_prof_final)",
-         "Command: `ncu --set full --clock-control none --import-source on -k regex:'pack_frames_kernel|convlstm_kernel|conv_igemm_kernel<16' -s 4 -c 6 python tools/run_window.py 2`.\n"
+    full("r02f_prof_k345.ncu-rep", "ncu --set full: the memory-/FP32-bound kernels of one window: K3 pack_frames, K5 convlstm, (K4 = final conv, see r02_prof_final)",
+         "Command: `ncu --set full --clock-control none --import-source on -k regex:'pack_frames_kernel|convlstm_kernel|conv_igemm_kernel<16' -s 5 -c 5 python tools/run_window.py 2` (K3 stage-1 launch, K5 3-cell launch, K3, K4 final conv, K3).\n"
          "pack_frames: reads 3n fp32 frames (24n B per low-res position; frames shared by adjacent calls hit L2), writes 16 B per 8-channel plane.\n"
          "convlstm (prev_state=None): 324 FMA + 15 transcendentals per pixel against 36 B -> FP32-FMA bound, not HBM bound (DESIGN 4d).", FP)
+    full("r02f_prof_tail.ncu-rep", "ncu --set full: fused RDB tail (default single-CTA kernel) at 5x360x640, final state of round 2",
+         "Command: `ncu --set full --clock-control none --import-source on -k regex:rdb_tail -s 48 -c 1 python tools/run_window.py 2`.")
+    for pr in ("0", "1"):
+        full(f"r02f_prof_conv_pair{pr}.ncu-rep", f"ncu --set full: x-stacked RDB convs 0..2 at 5x360x640, BIN_B200_PAIR={pr} ({'CTA-pair cta_group::2' if pr == '1' else 'single-CTA'} kernel), same box",
+             f"Command: `BIN_B200_PAIR={pr} ncu --set full --clock-control none --import-source on -k regex:'conv_igemm_kernel<\\(int\\)32' -s 144 -c 3 python tools/run_window.py 2`.\n"
+             "Algorithmic FLOPs per launch: 2*5*230400*(96+32c)*32*9; bytes: reads 5*230400*(192+64c), writes 5*230400*64.")
     for pr in ("0", "1"):
         full(f"r02b_prof_tail_pair{pr}.ncu-rep", f"ncu --set full: fused RDB tail at 5x360x640, BIN_B200_PAIR={pr} ({'CTA-pair cta_group::2' if pr == '1' else 'single-CTA'} kernel), same box",
              f"Command: `BIN_B200_PAIR={pr} ncu --set full --clock-control none --import-source on -k regex:rdb_tail -s 48 -c 1 python tools/run_window.py 2`.\n"
              "Algorithmic bytes per launch: reads 5*230400*384 B (x + g0..g2) + residual (L2), writes 5*230400*192 B; FLOPs 2*5*230400*(192*32*9 + 224*96).")
-        full(f"r02b_prof_conv_pair{pr}.ncu-rep", f"ncu --set full: x-stacked RDB convs 0..2 at 5x360x640, BIN_B200_PAIR={pr}, same box",
-             f"Command: `BIN_B200_PAIR={pr} ncu --set full --clock-control none --import-source on -k regex:'conv_igemm_kernel<32' -s 144 -c 3 python tools/run_window.py 2`.\n"
-             "Algorithmic FLOPs per launch: 2*5*230400*(96+32c)*32*9; bytes: reads 5*230400*(192+64c), writes 5*230400*64.")
