@@ -453,6 +453,15 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
 #pragma unroll
         for (int g0 = 0; g0 < NT; g0 += GRP) {
           uint32_t v[(SX ? 3 : 1) * GRP];
+#ifdef BIN_B200_TOOLS      // epilogue ablations for the timeline tool (timing only, results are garbage): BIN_B200_DEBUG bits 5..8
+          const bool abl_ld = p.debug & 32, abl_bias = p.debug & 64, abl_shfl = p.debug & 128, abl_st = p.debug & 256;
+          if (abl_ld) {
+#pragma unroll
+            for (int i = 0; i < (SX ? 3 : 1) * GRP; ++i) v[i] = lane + i;
+          } else
+#else
+          constexpr bool abl_bias = false, abl_shfl = false, abl_st = false;
+#endif
 #pragma unroll
           for (int j = 0; j < GRP / 16; ++j) {
             if constexpr (SX) {
@@ -472,9 +481,9 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
               // out[p] = D[p][kx=0] + D[p+1][kx=1] + D[p+2][kx=2]; p+1, p+2 are lanes +1, +2 of this warp
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[GRP + 16 * j + i]), 1);
-                const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[2 * GRP + 16 * j + i]), 2);
-                f[i] = ((__uint_as_float(v[16 * j + i]) + b1) + b2) * kAcc + sbias[n0 + i];
+                const float b1 = abl_shfl ? __uint_as_float(v[GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[GRP + 16 * j + i]), 1);
+                const float b2 = abl_shfl ? __uint_as_float(v[2 * GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[2 * GRP + 16 * j + i]), 2);
+                f[i] = ((__uint_as_float(v[16 * j + i]) + b1) + b2) * kAcc + (abl_bias ? 0.25f : sbias[n0 + i]);
               }
             } else {
 #pragma unroll
@@ -521,7 +530,7 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
                   o.z = pack_h2(f[h * 8 + 4], f[h * 8 + 5]);
                   o.w = pack_h2(f[h * 8 + 6], f[h * 8 + 7]);
                   const size_t off = ((((size_t)b * p.out_planes + p.out_plane0 + cpl + h) * p.H + y) * p.W + x) * 8;
-                  if (cpl + h < p.store_planes) *reinterpret_cast<uint4*>(p.out + off) = o;
+                  if (cpl + h < p.store_planes && !abl_st) *reinterpret_cast<uint4*>(p.out + off) = o;
                 }
               }
             }
