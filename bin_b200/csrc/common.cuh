@@ -53,6 +53,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned long long tag = 0ull) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef BIN_B200_TOOLS
+    if (tag >> 63) __nanosleep(64);          // experiment: polite polling (tag bit 63)
+#endif
     if (++spins > BIN_SPIN_LIMIT) {
       printf("bin_b200: mbarrier watchdog (block %d/%d thread %d bar %p parity %u tag %llx)\n", blockIdx.x, gridDim.x,
              threadIdx.x, (void*)bar, parity, tag);

@@ -150,8 +150,9 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
   const int tqstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int tqn = PAIR ? (p.ntiles + 1) >> 1 : p.ntiles;
   // watchdog tag: instantiation | role | pipeline iteration
-  constexpr unsigned long long kTag = ((unsigned long long)NT << 48) | ((unsigned long long)KS << 44) | ((unsigned long long)EPI << 40) |
-                                      ((unsigned long long)SX << 38) | ((unsigned long long)X3 << 37) | ((unsigned long long)PAIR << 36);
+  constexpr unsigned long long kTag0 = ((unsigned long long)NT << 48) | ((unsigned long long)KS << 44) | ((unsigned long long)EPI << 40) |
+                                       ((unsigned long long)SX << 38) | ((unsigned long long)X3 << 37) | ((unsigned long long)PAIR << 36);
+  const unsigned long long kTag = kTag0 | ((p.debug & 512) ? (1ull << 63) : 0ull);   // tools build: bit 63 = polite polling experiment
   auto tile_at = [&](int tq, bool& live) {
     int t = PAIR ? 2 * tq + (int)rank : tq;
     live = t < p.ntiles;
