@@ -122,13 +122,13 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
     for (int i = 0; i <= kRtChunks; ++i) mbar_init(&ctrl->wfull[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctrl->conv_full[i], STREAMS ? 1 : 2);   // tcgen05.commit of the stream's / of each MMA warp
-      mbar_init(&ctrl->conv_empty[i], 128);    // the four epilogue-A warps
-      mbar_init(&ctrl->h_full[i], 128);
+      mbar_init(&ctrl->conv_empty[i], 4);      // the four epilogue-A warps, one arrival per warp (128 threads arriving on
+      mbar_init(&ctrl->h_full[i], 4);          // one mbarrier serialise in the shared-memory atomic unit)
       mbar_init(&ctrl->h_empty[i], 1);
     }
     for (int i = 0; i < 3; ++i) {
       mbar_init(&ctrl->lff_full[i], 1);
-      mbar_init(&ctrl->lff_empty[i], 128);     // the four epilogue-B warps
+      mbar_init(&ctrl->lff_empty[i], 4);       // the four epilogue-B warps, one arrival per warp
     }
     ctrl->issued = 0;
     fence_barrier_init();
@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
       for (int j = 0; j < 6; ++j) tmem_ld16(taddr + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&ctrl->conv_empty[as]);                              // accumulator is in registers: release it now
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctrl->conv_empty[as]);               // accumulator is in registers: release it now
       // out[p] = D[p][kx=0] + D[p+1][kx=1] + D[p+2][kx=2]  (p+1, p+2 are lanes +1, +2: one warp = one tile row)
       uint4 o[4];
       uint32_t* ow = reinterpret_cast<uint32_t*>(o);
@@ -377,7 +378,8 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
         for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(h + k * kRtHPlane) = o[k];
       }
       fence_proxy_async();                                             // generic-proxy stores -> visible to tcgen05.mma
-      mbar_arrive(&ctrl->h_full[as]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctrl->h_full[as]);
       if (warp == 4 && lane == 0) rt_rec(p, 2, tl, 3);
     }
   } else if (warp >= 8) {
@@ -411,7 +413,8 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
         tmem_ld_wait();
         if (g0 == 48) {                                                // all 96 columns are in registers
           tc_fence_before();
-          mbar_arrive(&ctrl->lff_empty[lb]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctrl->lff_empty[lb]);
         }
 #pragma unroll
         for (int j = 0; j < 48; ++j) v[j] = __shfl_down_sync(0xffffffffu, v[j], 1);   // accumulator row p holds pixel p-1
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
 //                 (cp.async.bulk.tensor...cta_group::2 with the leader's barrier address from mapa)
 //   empty[slot], conv_full, lff_full, h_empty   one tcgen05.commit...multicast::cluster (mask 0b11) signals the barrier
 //                 at the same offset in BOTH CTAs -> producers and epilogues only ever wait on CTA-local barriers
-//   h_full, lff_empty   leader's barriers counting 256 arrivals: the 128 epilogue threads of each CTA
+//   h_full, lff_empty   leader's barriers counting 8 arrivals: one per epilogue warp of each CTA
 //                 (mbarrier.arrive.release.cluster on the mapa'd address; the MMA warps wait with acquire.cluster)
 //   wready        leader's barrier, 1 arrival from the peer once ITS weight halves have landed
 // Tile pair q = cluster + j * nclusters; CTA r owns tile 2q + r (a cluster with an odd tile count runs a dummy last
@@ -510,12 +513,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) rdb_tail_pai
     mbar_init(&ctrl->wready, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctrl->conv_full[i], 1);
-      mbar_init(&ctrl->h_full[i], 256);        // epilogue-A threads of both CTAs (used in the leader)
+      mbar_init(&ctrl->h_full[i], 8);          // epilogue-A warps of both CTAs, one arrival per warp (used in the leader)
       mbar_init(&ctrl->h_empty[i], 1);
     }
     for (int i = 0; i < 3; ++i) {
       mbar_init(&ctrl->lff_full[i], 1);
-      mbar_init(&ctrl->lff_empty[i], 256);     // epilogue-B threads of both CTAs (used in the leader)
+      mbar_init(&ctrl->lff_empty[i], 8);       // epilogue-B warps of both CTAs, one arrival per warp (used in the leader)
     }
     fence_barrier_init();
   }
@@ -592,9 +595,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) rdb_tail_pai
     uint32_t k = 0, n = 0;
     for (int j = (int)Y; (int)(cluster + j * nclusters) < npt; j += 2, ++n) {
       const uint32_t lb = (uint32_t)j % 3;
-      // conv[Y] is free in BOTH CTAs: this warp waited for the g3 tiles of its previous tile pair (256 arrivals), which
+      // conv[Y] is free in BOTH CTAs: this warp waited for the g3 tiles of its previous tile pair (8 warp arrivals), which
       // the epilogue-A warps write after reading the accumulator.  The rotating LFF accumulator was released three
-      // tile pairs ago (256 arrivals as well).
+      // tile pairs ago (8 arrivals as well).
       mbar_wait_cluster(&ctrl->lff_empty[lb], (((uint32_t)j / 3) & 1) ^ 1);
       const uint32_t d_conv = tmem_base + Y * kRtN;
       const uint32_t d_lff = tmem_base + kRtLffCol0 + lb * kRtN;
@@ -687,7 +690,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) rdb_tail_pai
         for (int kk = 0; kk < 4; ++kk) *reinterpret_cast<uint4*>(h + kk * kRtHPlane) = o[kk];
       }
       fence_proxy_async();                                             // generic-proxy stores -> visible to tcgen05.mma
-      mbar_arrive_cluster(hfull0 + as * 8);                            // the accumulator has been read, the g3 tile is written
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(hfull0 + as * 8);             // the accumulator has been read, the g3 tile is written
     }
   } else if (warp >= 8) {
     // ========================================================== epilogue B: LFF accumulator + bias + x -> x', both CTAs
@@ -716,7 +720,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) rdb_tail_pai
         tmem_ld_wait();
         if (g0 == 48) {                                                // all 96 columns are in registers
           tc_fence_before();
-          mbar_arrive_cluster(lffempty0 + lb * 8);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(lffempty0 + lb * 8);
         }
 #pragma unroll
         for (int i = 0; i < 48; ++i) v[i] = __shfl_down_sync(0xffffffffu, v[i], 1);   // accumulator row p holds pixel p-1
