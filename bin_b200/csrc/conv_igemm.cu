@@ -476,6 +476,7 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
             }
           }
           tmem_ld_wait();
+          if (warp == 4 && lane == 0 && g0 == 0) dbg_rec(p, 2, acc_it, 3);        // tools build: TMEM loads have landed
 #pragma unroll
           for (int j = 0; j < GRP / 16; ++j) {
             const int n0 = g0 + 16 * j;

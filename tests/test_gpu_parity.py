@@ -313,10 +313,11 @@ def test_cta_pair_kernels_bit_identical_to_single_cta():
         "    for o in outs: h.update(o.cpu().numpy().tobytes())\n"
         "print('HASH', h.hexdigest())\n" % ROOT)
     got = {}
-    for tag, env in (("single", {"BIN_B200_PAIR": "0", "BIN_B200_MSPLIT": "0"}), ("pair", {"BIN_B200_PAIR": "1", "BIN_B200_MSPLIT": "0"}),
-                     ("msplit", {"BIN_B200_PAIR": "0", "BIN_B200_MSPLIT": "1"}), ("pair+msplit", {"BIN_B200_PAIR": "1", "BIN_B200_MSPLIT": "1"}),
-                     ("quad", {"BIN_B200_QUAD": "1"}), ("quad+zigzag", {"BIN_B200_QUAD": "1", "BIN_B200_ZIGZAG": "1"}),
-                     ("zigzag", {"BIN_B200_ZIGZAG": "1"}), ("pair+zigzag", {"BIN_B200_PAIR": "1", "BIN_B200_ZIGZAG": "1"})):
+    base = {"BIN_B200_PAIR": "0", "BIN_B200_MSPLIT": "0", "BIN_B200_QUAD": "0", "BIN_B200_ZIGZAG": "0"}
+    for tag, over in (("two-warp", {}), ("default(quad)", {"BIN_B200_QUAD": "1"}), ("pair", {"BIN_B200_PAIR": "1"}),
+                      ("msplit", {"BIN_B200_MSPLIT": "1"}), ("pair+msplit", {"BIN_B200_PAIR": "1", "BIN_B200_MSPLIT": "1"}),
+                      ("quad+zigzag", {"BIN_B200_QUAD": "1", "BIN_B200_ZIGZAG": "1"}), ("pair+zigzag", {"BIN_B200_PAIR": "1", "BIN_B200_ZIGZAG": "1"})):
+        env = dict(base, **over)
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, (tag, r.stderr[-2000:])
         got[tag] = r.stdout.strip().split("HASH")[-1].strip()

@@ -50,7 +50,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         res["window_ms"] = round(t(lambda: net(*fr), reps=10), 3)
     print(json.dumps(res))
 else:
-    cfgs = [{}, {"BIN_B200_QUAD": "1"}, {"BIN_B200_MSPLIT": "1"}, {"BIN_B200_PAIR": "1"}, {}, {"BIN_B200_QUAD": "1"},
+    cfgs = [{"BIN_B200_QUAD": "0"}, {"BIN_B200_QUAD": "1"}, {"BIN_B200_QUAD": "0", "BIN_B200_MSPLIT": "1"},
+            {"BIN_B200_QUAD": "0", "BIN_B200_PAIR": "1"}, {"BIN_B200_QUAD": "0"}, {"BIN_B200_QUAD": "1"},
             {"BIN_B200_QUAD": "1", "BIN_B200_STAGE_MMAS": "24"}]
     for cfg in cfgs:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, **cfg), capture_output=True,

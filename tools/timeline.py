@@ -20,7 +20,7 @@ _lib.check(_lib.lib().bin_tools_debug_timeline(buf, 3 * 4096))
 a = list(buf)
 def role(r, n, k): return [[a[r * 4096 + i * 4 + j] for j in range(k)] for i in range(n)]
 nch = cin // 32
-mma = role(1, 17 * nch, 3); prod = role(0, 17 * nch, 2); epi = role(2, 34, 3)
+mma = role(1, 17 * nch, 3); prod = role(0, 17 * nch, 2); epi = role(2, 34, 4)
 t0 = min(v for v in (prod[0][0], mma[0][0], epi[0][0]) if v)
 print("MMA per-stage: [wait_start, wait_done, issued] rel cycles; first 14 and a steady-state slice")
 for i in list(range(0, 10)) + list(range(30, 42)):
@@ -30,5 +30,6 @@ for i in list(range(0, 8)) + list(range(30, 38)):
     print("prod", i, [v - t0 for v in prod[i]], " wait=%d" % (prod[i][1] - prod[i][0]))
 print("epilogue per tile: [wait_start, acc_ready, done]")
 for i in list(range(0, 6)) + list(range(20, 24)):
-    print("epi", i, [v - t0 for v in epi[i]], " wait=%d work=%d" % (epi[i][1] - epi[i][0], epi[i][2] - epi[i][1]))
+    print("epi", i, [v - t0 for v in epi[i][:3]], " wait=%d work=%d (tmem loads %d, math+stores+arrive %d)" %
+          (epi[i][1] - epi[i][0], epi[i][2] - epi[i][1], epi[i][3] - epi[i][1], epi[i][2] - epi[i][3]))
 print("total cycles block0:", max(v[2] for v in epi) - t0, " per tile:", (epi[30][2] - epi[10][2]) / 20.0)
