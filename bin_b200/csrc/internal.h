@@ -51,6 +51,7 @@ struct Options {
   bool pair;                 // BIN_B200_PAIR=1 selects the CTA-pair (cta_group::2) kernels (measured slower: opt-in)
   bool msplit;               // BIN_B200_MSPLIT: conv MMA warps split the tile's two accumulators instead of alternating stages
   bool quad;                 // BIN_B200_QUAD=0 falls back to two MMA warps in the x-stacked conv kernel (default: four)
+  bool tailq;                // BIN_B200_TAILQ: two MMA warps per tile stream in rdb_tail_kernel (448 threads)
   bool zigzag;               // BIN_B200_ZIGZAG: consecutive RDB launches walk the tiles in opposite directions (L2 reuse)
   int stage_mmas;            // BIN_B200_STAGE_MMAS: target MMAs per pipeline stage of the conv kernel (default 12)
   size_t band_budget;        // BIN_B200_BAND_BUDGET_KB (L2 band walker; default: one band)

@@ -81,6 +81,7 @@ struct RtCtrl {
   uint64_t h_full[2], h_empty[2];
   uint32_t tmem_base;
   volatile uint32_t issued;       // stage items issued so far (hand-off between the two MMA warps)
+  volatile uint32_t issued2[2];   // QUADT: items issued so far per tile stream (hand-off between the stream's two MMA warps)
 };
 static_assert(sizeof(RtCtrl) <= 512, "ctrl block");
 
@@ -102,8 +103,14 @@ __device__ __forceinline__ float2 rt_unpack_h2(uint32_t u) {
 // one conv accumulator each) that share the tensor pipe, the LFF accumulators and the epilogue warps; nothing orders
 // one stream against the other, so one stream's barrier polls and its wait for the g3 tile are covered by the other's
 // MMAs.  !STREAMS: the two MMA warps alternate the items of ONE tile stream through a hand-off counter.
-template <bool STREAMS>
-__global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant__ RdbTailParams p) {
+// QUADT (448 threads, STREAMS only): each tile stream gets TWO MMA warps that alternate the stream's 8-MMA items (warp
+// (Y, P) owns ring slot Y + 2 P and the items of parity P; strict item order through issued2[Y]; the warp of the last
+// item also issues the tile's tail step).  A single warp per stream serialises barrier wait -> data wait -> issue, and
+// a lone issuer sustains only one MMA per ~80 cycles; with two warps per stream one issues while the other already
+// waits for the next slot.  Per-accumulator MMA order is unchanged -> bit-identical results.
+template <bool STREAMS, bool QUADT = false>
+__global__ void __launch_bounds__(QUADT ? 448 : 384, 1) rdb_tail_kernel(const __grid_constant__ RdbTailParams p) {
+  static_assert(!QUADT || STREAMS, "QUADT refines the two-stream scheme");
   extern __shared__ __align__(1024) uint8_t smem[];
   RtCtrl* ctrl = reinterpret_cast<RtCtrl*>(smem);
   float* sb_conv = reinterpret_cast<float*>(smem + 512);           // 32 floats
@@ -121,16 +128,17 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
     for (int i = 0; i < kRtStages; ++i) { mbar_init(&ctrl->full[i], 1); mbar_init(&ctrl->empty[i], 1); }
     for (int i = 0; i <= kRtChunks; ++i) mbar_init(&ctrl->wfull[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&ctrl->conv_full[i], STREAMS ? 1 : 2);   // tcgen05.commit of the stream's / of each MMA warp
+      mbar_init(&ctrl->conv_full[i], (STREAMS && !QUADT) ? 1 : 2);   // tcgen05.commit of the stream's warp / of each MMA warp
       mbar_init(&ctrl->conv_empty[i], 4);      // the four epilogue-A warps, one arrival per warp (128 threads arriving on
       mbar_init(&ctrl->h_full[i], 4);          // one mbarrier serialise in the shared-memory atomic unit)
       mbar_init(&ctrl->h_empty[i], 1);
     }
     for (int i = 0; i < 3; ++i) {
-      mbar_init(&ctrl->lff_full[i], 1);
+      mbar_init(&ctrl->lff_full[i], QUADT ? 2 : 1);   // QUADT: a commit only tracks the committing thread's MMAs -> both warps commit
       mbar_init(&ctrl->lff_empty[i], 4);       // the four epilogue-B warps, one arrival per warp
     }
     ctrl->issued = 0;
+    ctrl->issued2[0] = ctrl->issued2[1] = 0;
     fence_barrier_init();
   }
   if (threadIdx.x < 32) sb_conv[threadIdx.x] = p.b_conv[threadIdx.x];
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
                     &ctrl->full[slot], x0 * 8, y0, seg1 ? p.plane0_1 + (c - 3) * kKPL : p.plane0_0 + c * kKPL, b);
       }
     }
-  } else if (warp == 1 || warp == 3) {
+  } else if (warp == 1 || warp == 3 || (QUADT && warp >= 12)) {
     // ========================================================== MMA issuers (warp converged, one elected lane)
     // Measured on B200: an mbarrier poll costs 200-350 cycles even when the phase is complete and the tcgen05 queue is
     // shallow, so a warp that polls between its 8-MMA items idles the tensor pipe.  Two warps alternate items: stage
@@ -188,7 +196,8 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
     // targets an accumulator nobody else touches: warp B issues it after its last item, outside the ordered sequence.
     // (Tried and slower, see DESIGN.md: one issuing warp fed by a "scout" warp that does all the polling; 16-MMA items;
     // a 5-slot ring.)
-    const uint32_t Y = warp >> 1;
+    const uint32_t Y = (QUADT && warp >= 12) ? (uint32_t)(warp - 12) : (uint32_t)(warp >> 1);   // QUADT: warps 1, 12 -> stream 0; 3, 13 -> stream 1
+    const uint32_t P = (QUADT && warp >= 12) ? 1u : 0u;                            // QUADT: item parity this warp issues
     constexpr uint32_t idesc = umma_idesc_f16(128, kRtN);
     constexpr uint32_t D_HI = (128u >> 4) | (1u << 14);                // SBO = 128 B, descriptor version 1
     constexpr uint32_t A_LBO = ((uint32_t)kRtAPlane >> 4) << 16;
@@ -263,7 +272,44 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
       }
       __syncwarp();
     };
-    if constexpr (STREAMS) {
+    if constexpr (STREAMS && QUADT) {
+      uint32_t k = 0, n = 0;
+      for (uint32_t tl2 = Y; (int)(blockIdx.x + tl2 * gridDim.x) < p.ntiles; tl2 += 2, ++n) {
+        const uint32_t lb = tl2 % 3;
+        if (P == 0) {
+          // the warp of item 0 zeroes both accumulators: the rotating LFF accumulator was released three tiles ago, and
+          // conv[Y] is free once epilogue A has read the stream's previous tile (= its g3 tile is written: h_full)
+          mbar_wait(&ctrl->lff_empty[lb], ((tl2 / 3) & 1) ^ 1);
+          if (n > 0) mbar_wait(&ctrl->h_full[Y], (n - 1) & 1);
+        }
+        const uint32_t d_conv = tmem_base + Y * kRtN;
+        const uint32_t d_lff = tmem_base + kRtLffCol0 + lb * kRtN;
+        for (int c = 0; c < kRtChunks; ++c, ++k) {
+          if ((uint32_t)(c & 1) != P) continue;                        // 6 items per tile: item parity = chunk parity
+          const uint32_t slot = Y + 2 * P;                             // this warp's own ring slot
+          if (warp == 1 && lane == 0) rt_rec(p, 1, k >> 1, 0);
+          mbar_wait(&ctrl->full[slot], (k >> 1) & 1);
+          if (n == 0) mbar_wait(&ctrl->wfull[c], 0);
+          if (warp == 1 && lane == 0) rt_rec(p, 1, k >> 1, 1);
+          while (ctrl->issued2[Y] < k) __nanosleep(20);                // item k-1 of this stream has been issued
+          tc_fence_after();
+          if (warp == 1 && lane == 0) rt_rec(p, 1, k >> 1, 2);
+          issue_item(slot, c, d_conv, d_lff, c == kRtChunks - 1, Y);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ctrl->issued2[Y] = k + 1;
+          if (warp == 1 && lane == 0) rt_rec(p, 1, k >> 1, 3);
+        }
+        if (P == 0) {                                                  // this warp's share of the tile's MMAs (items 0, 2, 4)
+          if (elect_one()) {
+            umma_commit(&ctrl->conv_full[Y]);
+            umma_commit(&ctrl->lff_full[lb]);
+          }
+          __syncwarp();
+        }
+        if (P == 1) tail_item(tl2);                                    // waits for this tile's g3, then 2 MMAs (+ its commits)
+      }
+    } else if constexpr (STREAMS) {
       uint32_t k = 0, n = 0;
       for (uint32_t tl2 = Y; (int)(blockIdx.x + tl2 * gridDim.x) < p.ntiles; tl2 += 2, ++n) {
         const uint32_t lb = tl2 % 3;
@@ -382,7 +428,7 @@ __global__ void __launch_bounds__(384, 1) rdb_tail_kernel(const __grid_constant_
       if (lane == 0) mbar_arrive(&ctrl->h_full[as]);
       if (warp == 4 && lane == 0) rt_rec(p, 2, tl, 3);
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ========================================================== epilogue B: LFF accumulator + bias + x -> x'
     const int q = warp & 3;
     uint32_t tl = 0;
@@ -801,6 +847,14 @@ int launch_rdb_tail(const bin_act_t& x, int x_plane0, const bin_act_t& g, int g_
     const int npt = (p.ntiles + 1) / 2, maxc = num_sms() / 2;
     const int nclusters = npt < maxc ? npt : maxc;
     rdb_tail_pair_kernel<<<2 * nclusters, 384, kRpSmem, s>>>(p);
+    BIN_CUDA_OK(cudaGetLastError());
+    return BIN_OK;
+  }
+  if (streams && options().tailq) {
+    static std::atomic<unsigned long long> opted_q{0};   // per device
+    BIN_TRY(ensure_dynamic_smem(rdb_tail_kernel<true, true>, kRtSmem, opted_q));
+    const int sq = num_sms();
+    rdb_tail_kernel<true, true><<<p.ntiles < sq ? p.ntiles : sq, 448, kRtSmem, s>>>(p);
     BIN_CUDA_OK(cudaGetLastError());
     return BIN_OK;
   }

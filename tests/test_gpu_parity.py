@@ -313,8 +313,9 @@ def test_cta_pair_kernels_bit_identical_to_single_cta():
         "    for o in outs: h.update(o.cpu().numpy().tobytes())\n"
         "print('HASH', h.hexdigest())\n" % ROOT)
     got = {}
-    base = {"BIN_B200_PAIR": "0", "BIN_B200_MSPLIT": "0", "BIN_B200_QUAD": "0", "BIN_B200_ZIGZAG": "0"}
-    for tag, over in (("two-warp", {}), ("default(quad)", {"BIN_B200_QUAD": "1"}), ("pair", {"BIN_B200_PAIR": "1"}),
+    base = {"BIN_B200_PAIR": "0", "BIN_B200_MSPLIT": "0", "BIN_B200_QUAD": "0", "BIN_B200_ZIGZAG": "0", "BIN_B200_TAILQ": "0"}
+    for tag, over in (("two-warp", {}), ("quad", {"BIN_B200_QUAD": "1"}), ("quad+tailq", {"BIN_B200_QUAD": "1", "BIN_B200_TAILQ": "1"}),
+                      ("tailq", {"BIN_B200_TAILQ": "1"}), ("pair", {"BIN_B200_PAIR": "1"}),
                       ("msplit", {"BIN_B200_MSPLIT": "1"}), ("pair+msplit", {"BIN_B200_PAIR": "1", "BIN_B200_MSPLIT": "1"}),
                       ("quad+zigzag", {"BIN_B200_QUAD": "1", "BIN_B200_ZIGZAG": "1"}), ("pair+zigzag", {"BIN_B200_PAIR": "1", "BIN_B200_ZIGZAG": "1"})):
         env = dict(base, **over)

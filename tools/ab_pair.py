@@ -39,11 +39,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     torch.cuda.synchronize()
     ms = sorted(ts)[len(ts) // 2]
     nbytes = B * h * w * 576
-    print(json.dumps({"pair": os.environ.get("BIN_B200_PAIR", "0"), "ms": round(ms, 4), "min_ms": round(min(ts), 4),
+    print(json.dumps({"pair": os.environ.get("BIN_B200_PAIR", "0"), "tailq": os.environ.get("BIN_B200_TAILQ", "0"), "ms": round(ms, 4), "min_ms": round(min(ts), 4),
                       "GBps_algorithmic": round(nbytes / ms / 1e6, 1), "bit_identical_to_layerwise": bool(torch.equal(out, out_ref)),
                       "max_abs_diff": (out.float() - out_ref.float()).abs().max().item()}))
 else:
-    for pair in ("0", "1", "0", "1"):
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, BIN_B200_PAIR=pair),
+    for cfg in ({"BIN_B200_PAIR": "0", "BIN_B200_TAILQ": "0"}, {"BIN_B200_PAIR": "0", "BIN_B200_TAILQ": "1"}, {"BIN_B200_PAIR": "1"},
+                {"BIN_B200_PAIR": "0", "BIN_B200_TAILQ": "0"}, {"BIN_B200_PAIR": "0", "BIN_B200_TAILQ": "1"}):
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, **cfg),
                            capture_output=True, text=True, timeout=300)
         print(r.stdout.strip() or r.stderr[-1500:], flush=True)
