@@ -48,41 +48,51 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons of ONE GPU sampled DURING the timed region (every rank samples its own GPU,
-    so the sampling load is the same on every rank)."""
+    """nvidia-smi clocks / throttle reasons of ONE GPU.  Every rank samples its own GPU.  The nvidia-smi process is started
+    BEFORE the warm-up (NVML initialisation enumerates every GPU of the node and must not fall into the timed region: with
+    one sampler per rank starting inside it, a 2-GPU run lost 20 %), polls at 5 Hz, and only the samples whose arrival time
+    lies inside [mark_begin, mark_end] are used."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.idx, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        t0, t1 = self.t0 or 0.0, (self.t1 or time.time()) + 0.2
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 8] or [r for (_, r) in self.rows if len(r) >= 8]
+        sm = sorted(int(float(r[1])) for r in rows if r[1].replace(".", "").isdigit())
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 8:
-                for n, v in zip(names, r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-        mx = next((int(float(r[2])) for r in self.rows if len(r) >= 8), None)
+        for r in rows:
+            for n, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = next((int(float(r[2])) for r in rows), None)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": mx,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -400,13 +410,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()                              # NVML start-up happens here, long before the timed region
     with torch.no_grad():
         for _ in range(args.warmup):
             for w_ in wins_dev:
                 net(*w_)
         barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
+        sampler.mark_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
@@ -414,6 +425,7 @@ def run_ours(args):
                 outs = net(*w_)
         e1.record()
         barrier()
+        sampler.mark_end()
         ms_dev = e0.elapsed_time(e1)
         clocks = sampler.stop()
         # ---- end-to-end: pinned host -> device, forward, 3 result images -> pinned host -----------
