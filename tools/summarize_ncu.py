@@ -15,11 +15,17 @@ os.makedirs(P, exist_ok=True)
 
 
 def short(name):
-    m = re.search(r"conv_igemm_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(int\))?(\d+), (?:\(bool\))?(\d)(?:, (?:\(bool\))?(\d))?(?:, (?:\(bool\))?(\d))?>", name)
+    m = re.search(r"conv_igemm_kernel<([^>]*)>", name)
     if m:
-        epi = {"0": "P8", "1": "PIXSHUF", "2": "FINAL"}[m.group(3)]
-        pair = ",PAIR" if m.group(6) == "1" else ""
-        return f"conv_igemm<NT={m.group(1)},KS={m.group(2)},{epi},SX={m.group(4)}{pair}>"
+        a = [re.sub(r"\((?:int|bool)\)", "", x).strip() for x in m.group(1).split(",")]
+        a += ["0"] * (7 - len(a))
+        epi = {"0": "P8", "1": "PIXSHUF", "2": "FINAL"}.get(a[2], a[2])
+        flags = ("" if a[4] == "0" else ",X3") + ("" if a[5] == "0" else ",PAIR") + ("" if a[6] == "0" else ",QUAD")
+        return f"conv_igemm<NT={a[0]},KS={a[1]},{epi},SX={a[3]}{flags}>"
+    m = re.search(r"rdb_tail_kernel<([^>]*)>", name)
+    if m:
+        a = [re.sub(r"\((?:int|bool)\)", "", x).strip() for x in m.group(1).split(",")] + ["0"]
+        return "rdb_tail_kernel<" + ("streams" if a[0] == "1" else "handoff") + (",quadt" if a[1] == "1" else "") + ">"
     return re.sub(r"\(.*", "", name).replace("binb::", "").replace("void ", "")
 
 
@@ -95,7 +101,7 @@ if tag == "r01":
          "Algorithmic FLOPs per launch: 2*5*230400*(192*32*9 + 224*96).")
 
 if tag == "r02":
-    launches("r02f_launches_window.csv", "r02_launches_window.md",
+    launches("r02m_launches_window.csv", "r02_launches_window.md",
              "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 227 -c 223 --csv python tools/run_window.py 2` "
              "(BIN_B200_GRAPH=0; skip = 4 batched weight-pack launches + the 223 launches of window 0; CTA-pair kernels on).")
     FP = [("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe % of peak"),
@@ -105,6 +111,9 @@ if tag == "r02":
          "Command: `ncu --set full --clock-control none --import-source on -k regex:'pack_frames_kernel|convlstm_kernel|conv_igemm_kernel<16' -s 5 -c 5 python tools/run_window.py 2` (K3 stage-1 launch, K5 3-cell launch, K3, K4 final conv, K3).\n"
          "pack_frames: reads 3n fp32 frames (24n B per low-res position; frames shared by adjacent calls hit L2), writes 16 B per 8-channel plane.\n"
          "convlstm (prev_state=None): 324 FMA + 15 transcendentals per pixel against 36 B -> FP32-FMA bound, not HBM bound (DESIGN 4d).", FP)
+    full("r02m_prof_conv_quad.ncu-rep", "ncu --set full: x-stacked RDB convs 0..2 at 5x360x640, final state (four MMA warps, 448 threads)",
+         "Command: `ncu --set full --clock-control none --import-source on -k regex:'conv_igemm_kernel<\\(int\\)32' -s 144 -c 3 python tools/run_window.py 2`.\n"
+         "Algorithmic FLOPs per launch: 2*5*230400*(96+32c)*32*9; bytes: reads 5*230400*(192+64c), writes 5*230400*64.")
     full("r02f_prof_tail.ncu-rep", "ncu --set full: fused RDB tail (default single-CTA kernel) at 5x360x640, final state of round 2",
          "Command: `ncu --set full --clock-control none --import-source on -k regex:rdb_tail -s 48 -c 1 python tools/run_window.py 2`.")
     for pr in ("0", "1"):
