@@ -14,7 +14,8 @@ net.load_state_dict(O.synth_state_dict(0), strict=True)
 net = net.cuda().eval()
 if "--fp32" in sys.argv:
     rdn.set_precision(net, "fp32")
-fr = [f.cuda() for f in O.synth_frames(6, 1, H, W, seed=1234, smooth=True)]
+BATCH = int(os.environ.get("RW_BATCH", "1"))          # windows per forward (batched along N)
+fr = [f.cuda() for f in O.synth_frames(6, BATCH, H, W, seed=1234, smooth=True)]
 with torch.no_grad():
     for i in range(n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -39,5 +40,5 @@ if "--graph" in sys.argv:
         g.replay()
         e1.record()
         torch.cuda.synchronize()
-        print(f"graph window {i}: {e0.elapsed_time(e1):.3f} ms", flush=True)
+        print(f"graph window {i}: {e0.elapsed_time(e1):.3f} ms" + (f" ({e0.elapsed_time(e1) / BATCH:.3f} ms per window, {BATCH} per forward)" if BATCH > 1 else ""), flush=True)
     print("graph outputs equal eager:", all(torch.equal(a, b) for a, b in zip(gouts, outs)))
