@@ -133,7 +133,7 @@ __device__ __forceinline__ void split_store(__half* base_hi, __half* base_lo, co
 // of this kernel), and half the resident-weight footprint (two more ring slots for the 160-channel conv).
 // Barriers as in rdb_tail_pair_kernel: `full` in the leader (2 x bytes, both CTAs' TMA credit it), `empty` / `tmem_full`
 // by multicast commit into both CTAs, `tmem_empty` in the leader counting the epilogue threads of both CTAs.
-// QUAD (448 threads; x-stacked fp16 convs, single CTA): FOUR MMA warps -- accumulator m of the tile is fed by the two warps
+// QUAD (448 threads; every fp16 conv with a P8 / PixelShuffle epilogue, single CTA): FOUR MMA warps -- accumulator m of the tile is fed by the two warps
 // (m, stage parity 0 / 1), which alternate stages and hand over through issued[m] exactly as the two warps of the default
 // scheme do.  The role timelines show a single issuing warp sustaining one MMA per ~82 cycles while two warps issuing
 // CONCURRENTLY reach the isolated rate (57); with four warps two are always issuing (one per accumulator) while the other
@@ -142,7 +142,7 @@ template <int NT, int KS, int EPI, bool SX, bool X3, bool PAIR = false, bool QUA
 __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using C = ConvCfg<NT, KS, SX>;
   static_assert(!PAIR || (SX && !X3 && EPI == BIN_EPI_P8), "the CTA-pair form exists for the x-stacked fp16 convs");
-  static_assert(!QUAD || (SX && !X3 && EPI == BIN_EPI_P8 && !PAIR), "the four-MMA-warp form exists for the x-stacked fp16 convs");
+  static_assert(!QUAD || (!X3 && !PAIR && EPI != BIN_EPI_FINAL), "the four-MMA-warp form exists for the fp16 P8 / PixelShuffle convs");
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   // tile sequence of this CTA: single CTA -> tiles blockIdx.x, +gridDim.x, ...; pair -> tile pair q = cluster, +nclusters, ...
   // with tile 2q + rank (the peer of an odd tail re-runs the last tile with its stores suppressed)
@@ -769,10 +769,11 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
       return BIN_OK;
     }
   }
-  if constexpr (kPairable) {
+  constexpr bool kQuadable = !X3 && EPI != BIN_EPI_FINAL;
+  if constexpr (kQuadable) {
     if (options().quad) {
       auto kq = conv_igemm_kernel<NT, KS, EPI, SX, X3, false, true>;
-      static std::atomic<unsigned long long> quad_opted{0};   // per device
+      static std::atomic<unsigned long long> quad_opted{0};   // per instantiation, per device
       BIN_TRY(ensure_dynamic_smem(kq, kSmemMax, quad_opted));
       const int gq = p.ntiles < num_sms() ? p.ntiles : num_sms();
       if (gq < 1) return BIN_OK;

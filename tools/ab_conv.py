@@ -44,15 +44,22 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     o96 = torch.empty(B, 12, h, w, 8, device=dev).half()
     ms = t(lambda: ops.conv_fwd(x, w96, b96, 3, 96, in0_planes=12, out=o96))
     res["conv3x3_96_ms"] = round(ms, 4); res["conv3x3_96_tflops"] = round(2.0 * B * h * w * 96 * 96 * 9 / ms / 1e9, 1)
+    w256 = ops.pack_conv_weight(torch.randn(256, 96, 3, 3, device=dev) / 864 ** 0.5, 256, 96)
+    b256 = ops.pad_bias(torch.zeros(256, device=dev), 256)
+    u = torch.empty(B, 8, 2 * h, 2 * w, 8, device=dev).half()
+    ms = t(lambda: ops.conv_fwd(x, w256, b256, 3, 256, in0_planes=12, epilogue=1, out=u))
+    res["upnet0_ms"] = round(ms, 4); res["upnet0_tflops"] = round(2.0 * B * h * w * 96 * 256 * 9 / ms / 1e9, 1)
+    x0 = torch.randn(B, 4, h, w, 8, device=dev).half()
+    w5 = ops.pack_conv_weight(torch.randn(96, 24, 5, 5, device=dev) / 600 ** 0.5, 96, 32)
+    ms = t(lambda: ops.conv_fwd(x0, w5, b96, 5, 96, in0_planes=4, out=o96))
+    res["sfenet1_ms"] = round(ms, 4)
     net = rdn.bin_stage4_lstm(); net.load_state_dict(O.synth_state_dict(0), strict=True); net = net.cuda().eval()
     fr = [f.cuda() for f in O.synth_frames(6, 1, 720, 1280, seed=1234, smooth=True)]
     with torch.no_grad():
         res["window_ms"] = round(t(lambda: net(*fr), reps=10), 3)
     print(json.dumps(res))
 else:
-    cfgs = [{"BIN_B200_QUAD": "0"}, {"BIN_B200_QUAD": "1"}, {"BIN_B200_QUAD": "0", "BIN_B200_MSPLIT": "1"},
-            {"BIN_B200_QUAD": "0", "BIN_B200_PAIR": "1"}, {"BIN_B200_QUAD": "0"}, {"BIN_B200_QUAD": "1"},
-            {"BIN_B200_QUAD": "1", "BIN_B200_STAGE_MMAS": "24"}]
+    cfgs = [{"BIN_B200_QUAD": "0"}, {"BIN_B200_QUAD": "1"}, {"BIN_B200_QUAD": "0"}, {"BIN_B200_QUAD": "1"}]
     for cfg in cfgs:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, **cfg), capture_output=True,
                            text=True, timeout=600)
