@@ -771,7 +771,9 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
   }
   constexpr bool kQuadable = !X3 && EPI != BIN_EPI_FINAL;
   if constexpr (kQuadable) {
-    if (options().quad) {
+    // (not with a residual / accumulate epilogue: its prefetch registers do not fit under the 448-thread bound without
+    // spills, and the data-gradient convs of the training step measured 1.5 % slower with it)
+    if (options().quad && (SX || a.res.ptr == nullptr)) {
       auto kq = conv_igemm_kernel<NT, KS, EPI, SX, X3, false, true>;
       static std::atomic<unsigned long long> quad_opted{0};   // per instantiation, per device
       BIN_TRY(ensure_dynamic_smem(kq, kSmemMax, quad_opted));
