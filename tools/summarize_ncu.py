@@ -101,7 +101,7 @@ if tag == "r01":
          "Algorithmic FLOPs per launch: 2*5*230400*(192*32*9 + 224*96).")
 
 if tag == "r02":
-    launches("r02m_launches_window.csv", "r02_launches_window.md",
+    launches("r02p_launches_window.csv", "r02_launches_window.md",
              "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 227 -c 223 --csv python tools/run_window.py 2` "
              "(BIN_B200_GRAPH=0; skip = 4 batched weight-pack launches + the 223 launches of window 0; CTA-pair kernels on).")
     FP = [("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe % of peak"),
