@@ -402,14 +402,34 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
     };
     frame_load(blockIdx.x, fv);
     const uint32_t tempty0 = PAIR ? mapa_u32(smem_u32(&ctrl->tmem_empty[0]), 0) : 0u;   // the LEADER's barriers
+    // Tile coordinates are advanced incrementally (mixed-radix add of the per-iteration step) instead of being decoded
+    // with six integer divisions per tile: with four MMA warps the epilogue is the kernel's critical path and those
+    // divisions were ~300 cycles of it per tile.  (Pair / reversed launches keep the division form.)
+    constexpr bool kIncr = !PAIR;
+    int c_nh = 0, c_tx = 0, c_ty = 0, c_b = 0, d_nh = 0, d_tx = 0, d_ty = 0, d_b = 0;
+    if (kIncr && !p.reverse) {
+      int t = tq0;
+      c_nh = t % p.nh; t /= p.nh; c_tx = t % p.tiles_x; t /= p.tiles_x; c_ty = t % p.tiles_y; c_b = t / p.tiles_y;
+      t = tqstep;
+      d_nh = t % p.nh; t /= p.nh; d_tx = t % p.tiles_x; t /= p.tiles_x; d_ty = t % p.tiles_y; d_b = t / p.tiles_y;
+    }
     for (int tq = tq0; tq < tqn; tq += tqstep, ++acc_it) {
-      bool live;
-      const int tile = tile_at(tq, live);
-      int t = tile;
-      const int nh = t % p.nh; t /= p.nh;
-      const int txi = t % p.tiles_x; t /= p.tiles_x;
-      const int tyi = t % p.tiles_y;
-      const int b = p.b0 + t / p.tiles_y;
+      bool live = true;
+      int tile, nh, txi, tyi, b;
+      if (kIncr && !p.reverse) {
+        tile = tq; nh = c_nh; txi = c_tx; tyi = c_ty; b = p.b0 + c_b;
+        c_nh += d_nh; if (c_nh >= p.nh) { c_nh -= p.nh; ++c_tx; }            // next tile's coordinates
+        c_tx += d_tx; if (c_tx >= p.tiles_x) { c_tx -= p.tiles_x; ++c_ty; }
+        c_ty += d_ty; if (c_ty >= p.tiles_y) { c_ty -= p.tiles_y; ++c_b; }
+        c_b += d_b;
+      } else {
+        tile = tile_at(tq, live);
+        int t = tile;
+        nh = t % p.nh; t /= p.nh;
+        txi = t % p.tiles_x; t /= p.tiles_x;
+        tyi = t % p.tiles_y;
+        b = p.b0 + t / p.tiles_y;
+      }
       const int yend = p.y0 + p.ny;
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
       float fmean[(EPI == BIN_EPI_FINAL) ? 3 : 1];
