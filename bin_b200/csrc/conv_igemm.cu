@@ -138,20 +138,8 @@ __device__ __forceinline__ void split_store(__half* base_hi, __half* base_lo, co
 // scheme do.  The role timelines show a single issuing warp sustaining one MMA per ~82 cycles while two warps issuing
 // CONCURRENTLY reach the isolated rate (57); with four warps two are always issuing (one per accumulator) while the other
 // two wait on their next barrier.  The MMA order per accumulator is unchanged -> bit-identical results.
-// EPI2 (QUAD + x-stacked P8 convs): SIXTEEN epilogue warps instead of eight -- warp (accumulator m, lane quarter q, channel
-// half) handles 16 of the 32 output channels.  With four MMA warps the epilogue is the kernel's critical path, and its
-// ~450-instruction body is latency-bound with two warps per scheduler (ncu source sampling: 51 % of all samples spread
-// evenly over it); twice the warps halve it.  704 threads -> 93 registers per thread.
-template <bool QUAD, bool SX, int EPI>
-constexpr int conv_epi_split() { return (QUAD && SX && EPI == BIN_EPI_P8) ? 2 : 1; }
-template <bool QUAD, bool SX, int EPI>
-constexpr int conv_threads() { return kThreads + (QUAD ? 64 : 0) + (conv_epi_split<QUAD, SX, EPI>() - 1) * 256; }
-
 template <int NT, int KS, int EPI, bool SX, bool X3, bool PAIR = false, bool QUAD = false>
-__global__ void __launch_bounds__(conv_threads<QUAD, SX, EPI>(), 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
-  constexpr int kEpiSplit = conv_epi_split<QUAD, SX, EPI>();
-  constexpr int kEpiWarps = 8 * kEpiSplit;
-  constexpr int kMmaX = 4 + kEpiWarps;                         // first extra MMA warp of the QUAD scheme
+__global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using C = ConvCfg<NT, KS, SX>;
   static_assert(!PAIR || (SX && !X3 && EPI == BIN_EPI_P8), "the CTA-pair form exists for the x-stacked fp16 convs");
   static_assert(!QUAD || (!X3 && !PAIR && EPI != BIN_EPI_FINAL), "the four-MMA-warp form exists for the fp16 P8 / PixelShuffle convs");
@@ -200,7 +188,7 @@ __global__ void __launch_bounds__(conv_threads<QUAD, SX, EPI>(), 1) conv_igemm_k
     for (int i = 0; i < kMaxResidentChunks; ++i) mbar_init(&ctrl->wfull[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctrl->tmem_full[i], QUAD ? 4 : 2);        // one tcgen05.commit per MMA warp
-      mbar_init(&ctrl->tmem_empty[i], PAIR ? 16 : kEpiWarps);   // ONE arrival per epilogue warp (of both CTAs): 256 threads
+      mbar_init(&ctrl->tmem_empty[i], PAIR ? 16 : 8);      // ONE arrival per epilogue warp (of both CTAs): 256 threads
                                                            // arriving on one mbarrier serialise in the shared-memory
                                                            // atomic unit (~1 500 cycles per tile, measured by ablation)
     }
@@ -287,10 +275,10 @@ __global__ void __launch_bounds__(conv_threads<QUAD, SX, EPI>(), 1) conv_igemm_k
     // ========================================================== peer: tell the leader when this CTA's B halves have landed
     for (int c = 0; c < nchunks; ++c) mbar_wait(&ctrl->wfull[c], 0);
     if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctrl->wready), 0));
-  } else if ((warp == 1 || warp == 3 || (QUAD && warp >= kMmaX)) && rank == 0) {
+  } else if ((warp == 1 || warp == 3 || (QUAD && warp >= 12)) && rank == 0) {
     // ========================================================== MMA issuers (warp converged, one elected lane; PAIR: leader only)
-    const uint32_t Y = QUAD ? ((warp == 1 || warp == kMmaX) ? 0u : 1u) : (uint32_t)(warp >> 1);   // stage parity this warp issues
-    const uint32_t mq = (QUAD && warp >= kMmaX) ? 1u : 0u;                                      // QUAD: its accumulator
+    const uint32_t Y = QUAD ? ((warp == 1 || warp == 12) ? 0u : 1u) : (uint32_t)(warp >> 1);   // stage parity this warp issues
+    const uint32_t mq = (QUAD && warp >= 12) ? 1u : 0u;                                        // QUAD: its accumulator
     constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 256 : 128, C::NMMA);
     constexpr uint32_t D_HI = (128u >> 4) | (1u << 14);            // SBO=128 B, descriptor version 1
     constexpr uint32_t A_LBO = ((uint32_t)C::A_PLANE >> 4) << 16;
@@ -383,11 +371,10 @@ __global__ void __launch_bounds__(conv_threads<QUAD, SX, EPI>(), 1) conv_igemm_k
       }
       __syncwarp();
     }
-  } else if (warp >= 4 && warp < kMmaX) {
+  } else if (warp >= 4 && warp < 12) {
     // ========================================================== epilogue
     const int q = warp & 3;
-    const int m = ((warp - 4) >> 2) & 1;                // which 128-row accumulator of the tile
-    const int chalf = (warp - 4) >> 3;                  // EPI2: which half of the output channels (0 otherwise)
+    const int m = (warp - 4) >> 2;                      // which 128-row accumulator of the tile
     uint32_t acc_it = 0;
     // FINAL epilogue: the mean of the input frames (RDN.py:221/279/333) of tile t+1 is loaded while tile t is being
     // processed (one tile of software pipelining: a cold DRAM round trip per tile was the kernel's critical path).
@@ -485,12 +472,9 @@ __global__ void __launch_bounds__(conv_threads<QUAD, SX, EPI>(), 1) conv_igemm_k
       if constexpr (EPI == BIN_EPI_P8) {
         // TMEM loads are issued in batches (tcgen05.wait::ld waits for ALL outstanding loads, so one wait per
         // 16 columns serialised a ~200-cycle round trip six times per tile and made the LFF epilogue the bottleneck)
-        constexpr int GRP = SX ? 32 / kEpiSplit : (NT % 48 == 0 ? 48 : (NT % 32 == 0 ? 32 : 16));   // output channels per batch
-        constexpr int NTW = NT / kEpiSplit;                 // output channels per epilogue warp
-        const int gbase = chalf * NTW;
+        constexpr int GRP = SX ? 32 : (NT % 48 == 0 ? 48 : (NT % 32 == 0 ? 32 : 16));   // output channels per batch
 #pragma unroll
-        for (int gg = 0; gg < NTW; gg += GRP) {
-          const int g0 = gbase + gg;
+        for (int g0 = 0; g0 < NT; g0 += GRP) {
           uint32_t v[(SX ? 3 : 1) * GRP];
 #ifdef BIN_B200_TOOLS      // epilogue ablations for the timeline tool (timing only, results are garbage): BIN_B200_DEBUG bits 5..8
           const bool abl_ld = p.debug & 32, abl_bias = p.debug & 64, abl_shfl = p.debug & 128, abl_st = p.debug & 256;
@@ -815,7 +799,7 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
       BIN_TRY(ensure_dynamic_smem(kq, kSmemMax, quad_opted));
       const int gq = p.ntiles < num_sms() ? p.ntiles : num_sms();
       if (gq < 1) return BIN_OK;
-      kq<<<gq, conv_threads<true, SX, EPI>(), smem_bytes, s>>>(p);
+      kq<<<gq, kThreads + 64, smem_bytes, s>>>(p);
       BIN_CUDA_OK(cudaGetLastError());
       return BIN_OK;
     }
