@@ -176,40 +176,47 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const __grid_constant__
 
 // ------------------------------------------------------------------ element-wise helpers of the backward pass
 // dst += src on P8 plane ranges (fp16).
-__global__ void p8_add_kernel(__half* __restrict__ dst, int dplanes, int dplane0, const __half* __restrict__ src,
-                              int splanes, int splane0, int nplanes, int B, size_t hw) {
-  const size_t total = (size_t)B * nplanes * hw;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t px = i % hw;
-    const int pl = (i / hw) % nplanes;
-    const int b = i / (hw * nplanes);
-    uint4* d = reinterpret_cast<uint4*>(dst + (((size_t)b * dplanes + dplane0 + pl) * hw + px) * 8);
-    const uint4 sv = *reinterpret_cast<const uint4*>(src + (((size_t)b * splanes + splane0 + pl) * hw + px) * 8);
-    uint4 dv = *d;
-    __half2* dh = reinterpret_cast<__half2*>(&dv);
-    const __half2* sh = reinterpret_cast<const __half2*>(&sv);
+// grid = (pixel groups, planes, batch): no 64-bit div/mod per element, two 16-byte pixels in flight per thread
+__global__ void __launch_bounds__(256) p8_add_kernel(__half* __restrict__ dst, int dplanes, int dplane0,
+                                                     const __half* __restrict__ src, int splanes, int splane0, int hw) {
+  const int pl = blockIdx.y, b = blockIdx.z;
+  uint4* d = reinterpret_cast<uint4*>(dst + ((size_t)b * dplanes + dplane0 + pl) * (size_t)hw * 8);
+  const uint4* sp = reinterpret_cast<const uint4*>(src + ((size_t)b * splanes + splane0 + pl) * (size_t)hw * 8);
+  const int p0 = blockIdx.x * 512 + threadIdx.x, p1 = p0 + 256;
+  uint4 sv[2], dv[2];
+  if (p0 < hw) { sv[0] = __ldg(sp + p0); dv[0] = d[p0]; }
+  if (p1 < hw) { sv[1] = __ldg(sp + p1); dv[1] = d[p1]; }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int px = u ? p1 : p0;
+    if (px >= hw) continue;
+    __half2* dh = reinterpret_cast<__half2*>(&dv[u]);
+    const __half2* sh = reinterpret_cast<const __half2*>(&sv[u]);
 #pragma unroll
     for (int k = 0; k < 4; ++k) dh[k] = __hadd2(dh[k], sh[k]);
-    *d = dv;
+    d[px] = dv[u];
   }
 }
 // ReLU backward: dg *= (g > 0), both P8 plane ranges.
-__global__ void p8_relu_mask_kernel(__half* __restrict__ dg, int dplanes, int dplane0, const __half* __restrict__ g,
-                                    int gplanes, int gplane0, int nplanes, int B, size_t hw) {
-  const size_t total = (size_t)B * nplanes * hw;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t px = i % hw;
-    const int pl = (i / hw) % nplanes;
-    const int b = i / (hw * nplanes);
-    uint4* d = reinterpret_cast<uint4*>(dg + (((size_t)b * dplanes + dplane0 + pl) * hw + px) * 8);
-    const uint4 gv = *reinterpret_cast<const uint4*>(g + (((size_t)b * gplanes + gplane0 + pl) * hw + px) * 8);
-    uint4 dv = *d;
-    __half* dh = reinterpret_cast<__half*>(&dv);
-    const __half* gh = reinterpret_cast<const __half*>(&gv);
+__global__ void __launch_bounds__(256) p8_relu_mask_kernel(__half* __restrict__ dg, int dplanes, int dplane0,
+                                                           const __half* __restrict__ g, int gplanes, int gplane0, int hw) {
+  const int pl = blockIdx.y, b = blockIdx.z;
+  uint4* d = reinterpret_cast<uint4*>(dg + ((size_t)b * dplanes + dplane0 + pl) * (size_t)hw * 8);
+  const uint4* gp = reinterpret_cast<const uint4*>(g + ((size_t)b * gplanes + gplane0 + pl) * (size_t)hw * 8);
+  const int p0 = blockIdx.x * 512 + threadIdx.x, p1 = p0 + 256;
+  uint4 gv[2], dv[2];
+  if (p0 < hw) { gv[0] = __ldg(gp + p0); dv[0] = d[p0]; }
+  if (p1 < hw) { gv[1] = __ldg(gp + p1); dv[1] = d[p1]; }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int px = u ? p1 : p0;
+    if (px >= hw) continue;
+    __half* dh = reinterpret_cast<__half*>(&dv[u]);
+    const __half* gh = reinterpret_cast<const __half*>(&gv[u]);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (!(__half2float(gh[k]) > 0.f)) dh[k] = __float2half_rn(0.f);
-    *d = dv;
+    d[px] = dv[u];
   }
 }
 // PixelShuffle(2) backward: dU P8 (B, 8 planes, 2h, 2w) -> d(conv out) P8 (B, 32 planes, h, w), n = 4c+2i+j.
@@ -935,16 +942,16 @@ int launch_convlstm(const float* x, const float* c_prev, const float* h_prev, co
   return launch_convlstm_multi(c, 1, B, H, W, s);
 }
 int launch_p8_add(const bin_act_t& dst, int dplane0, const bin_act_t& src, int splane0, int nplanes, cudaStream_t s) {
-  const size_t hw = (size_t)dst.H * dst.W;
-  p8_add_kernel<<<grid_for((size_t)dst.B * nplanes * hw, 256), 256, 0, s>>>((__half*)dst.ptr, dst.planes, dplane0,
-      (const __half*)src.ptr, src.planes, splane0, nplanes, dst.B, hw);
+  const int hw = dst.H * dst.W;
+  const dim3 grid((unsigned)((hw + 511) / 512), (unsigned)nplanes, (unsigned)dst.B);
+  p8_add_kernel<<<grid, 256, 0, s>>>((__half*)dst.ptr, dst.planes, dplane0, (const __half*)src.ptr, src.planes, splane0, hw);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
 }
 int launch_relu_mask(const bin_act_t& dg, int dplane0, const bin_act_t& g, int gplane0, int nplanes, cudaStream_t s) {
-  const size_t hw = (size_t)dg.H * dg.W;
-  p8_relu_mask_kernel<<<grid_for((size_t)dg.B * nplanes * hw, 256), 256, 0, s>>>((__half*)dg.ptr, dg.planes, dplane0,
-      (const __half*)g.ptr, g.planes, gplane0, nplanes, dg.B, hw);
+  const int hw = dg.H * dg.W;
+  const dim3 grid((unsigned)((hw + 511) / 512), (unsigned)nplanes, (unsigned)dg.B);
+  p8_relu_mask_kernel<<<grid, 256, 0, s>>>((__half*)dg.ptr, dg.planes, dplane0, (const __half*)g.ptr, g.planes, gplane0, hw);
   BIN_CUDA_OK(cudaGetLastError());
   return BIN_OK;
 }
