@@ -175,30 +175,36 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
 }
 
 // dW[co][ci][tap] += (1/scale) * sum over CTAs of partial[cta][tp][ci - ci0][col]   (col = co, or kx*32+co in SX mode)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nctas, int ntaps, int n, int sx, int tap0,
-                                    int ci0, int cout, int cin, int kk, const float* __restrict__ scale,
-                                    float* __restrict__ dw) {
+// 256 threads = 64 elements x 4 slab groups: thread (e, grp) sums slabs grp, grp+4, ... with 8 independent partial sums
+// (the ~148 slab reads of an element are independent loads; a single dependent chain kept a handful in flight and made
+// this kernel as slow as the GEMM: 34 us per launch for 22 MB of slabs).  The four group sums are combined in a fixed
+// order through shared memory, so dW stays bit-reproducible.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int nctas, int ntaps, int n, int sx,
+                                                           int tap0, int ci0, int cout, int cin, int kk,
+                                                           const float* __restrict__ scale, float* __restrict__ dw) {
+  __shared__ float part[4][64];
   const int total = ntaps * 128 * n;
-  const float inv = 1.f / scale[0];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+  const int e = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + e;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (i < total) {
+    const float* src = partial + i;
+    int c = grp;
+    for (; c + 28 < nctas; c += 32) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += __ldg(src + (size_t)(c + 4 * u) * total);
+    }
+    for (int u = 0; c < nctas; c += 4, ++u) a[u] += __ldg(src + (size_t)c * total);
+  }
+  part[grp][e] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  __syncthreads();
+  if (grp == 0 && i < total) {
+    const float acc = (part[0][e] + part[1][e]) + (part[2][e] + part[3][e]);
     const int col = i % n, row = (i / n) % 128, tp = i / (n * 128);
     const int ci = ci0 + row;
     const int co = sx ? (col & 31) : col;
     const int tap = sx ? tp * 3 + (col >> 5) : tap0 + tp;
-    if (ci >= cin || co >= cout) continue;
-    // eight independent partial sums: the 148 slab reads of one element are independent loads, but a single dependent
-    // accumulation chain kept only a few of them in flight (34 us per launch = as much time as the GEMM itself; the
-    // slabs are 22 MB = 7 us at HBM speed).  The order is fixed, so dW stays bit-reproducible.
-    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float* src = partial + i;
-    int c = 0;
-    for (; c + 8 <= nctas; c += 8) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] += __ldg(src + (size_t)(c + u) * total);
-    }
-    for (; c < nctas; ++c) a[c & 7] += __ldg(src + (size_t)c * total);
-    const float acc = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-    dw[((size_t)co * cin + ci) * kk + tap] += acc * inv;
+    if (ci < cin && co < cout) dw[((size_t)co * cin + ci) * kk + tap] += acc / scale[0];
   }
 }
 
@@ -249,8 +255,8 @@ int launch_wgrad_impl(const bin_act_t& x0, int x0_plane0, int x0_planes, const b
       wgrad_kernel<<<grid, 256, smem_bytes, s>>>(p);
       BIN_CUDA_OK(cudaGetLastError());
       const int total = p.ntaps * 128 * n;
-      wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(partial_ws, grid, p.ntaps, n, p.sx, t0, cp * 8, cout, cin, ks * ks,
-                                                            scale, dw);
+      wgrad_reduce_kernel<<<(total + 63) / 64, 256, 0, s>>>(partial_ws, grid, p.ntaps, n, p.sx, t0, cp * 8, cout, cin, ks * ks,
+                                                           scale, dw);
       BIN_CUDA_OK(cudaGetLastError());
     }
   }
