@@ -64,6 +64,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
   }
 }
 
+// Polite wait for roles that are NOT on the latency-critical path (TMA producers waiting for a ring slot, epilogue warps
+// waiting for an accumulator): sleep between polls.  These warps spin for thousands of cycles per tile; on a power-capped
+// part (the pool's B200s run at 1.45-1.7 GHz under sw_power_cap) every issued instruction of a spin loop is clock taken
+// from the tensor pipe.
+__device__ __forceinline__ void mbar_wait_polite(uint64_t* bar, uint32_t parity, uint32_t ns, unsigned long long tag = 0ull) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > BIN_SPIN_LIMIT) {
+      printf("bin_b200: mbarrier watchdog (block %d/%d thread %d bar %p parity %u tag %llx)\n", blockIdx.x, gridDim.x,
+             threadIdx.x, (void*)bar, parity, tag);
+      __trap();
+    }
+  }
+}
+
 // NOTE (measured, round 2): letting ONE lane poll and parking the other 31 at __syncwarp() does NOT make a warp-wide
 // wait cheaper -- a wait on an already-completed phase still costs 300-450 cycles while the tensor pipe is streaming
 // operands from shared memory -- and it serialised the two tile streams of rdb_tail_kernel (0.21 -> 0.28 ms).  All lanes

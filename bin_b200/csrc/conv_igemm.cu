@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
         const int nu = (nunits - unit < cps) ? nunits - unit : cps;
         if ((it & 1u) == Y) {
           if (Y == 0) dbg_rec(p, 0, it >> 1, 0);
-          mbar_wait(&ctrl->empty[s], ph ^ 1, kTag | (1ull << 32) | it);
+          if (p.polite) mbar_wait_polite(&ctrl->empty[s], ph ^ 1, 200, kTag | (1ull << 32) | it);
+          else mbar_wait(&ctrl->empty[s], ph ^ 1, kTag | (1ull << 32) | it);
           if (Y == 0) dbg_rec(p, 0, it >> 1, 1);
           uint8_t* dst = stage0 + (size_t)s * stage_bytes;
           if (!PAIR || rank == 0) mbar_expect_tx(&ctrl->full[s], (uint32_t)((PAIR ? 2 : 1) * nu * unit_bytes));
@@ -465,7 +466,8 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
       }
       constexpr float kAcc = X3 ? (1.f / 256.f) : 1.f;      // X3 weights are packed scaled by 2^8
       if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 0);
-      mbar_wait(&ctrl->tmem_full[as], aph, kTag | (4ull << 32) | acc_it);
+      if (p.polite) mbar_wait_polite(&ctrl->tmem_full[as], aph, 40, kTag | (4ull << 32) | acc_it);
+      else mbar_wait(&ctrl->tmem_full[as], aph, kTag | (4ull << 32) | acc_it);
       if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + m * C::NMMA;
@@ -761,6 +763,7 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
   p.fr = a.fr;
   p.debug = options().debug;
   p.msplit = options().msplit ? 1 : 0;
+  p.polite = options().polite ? 1 : 0;
   p.reverse = (reverse && EPI == BIN_EPI_P8) ? 1 : 0;     // (the FINAL epilogue prefetches tile + gridDim.x: forward only)
 #ifdef BIN_B200_TOOLS
   if (p.debug & 8) {

@@ -63,6 +63,7 @@ struct alignas(64) RdbTailParams {
   __half* out; int out_planes, out_plane0;
   const __half* res; int res_planes, res_plane0;
   int reverse;                          // walk the tiles last-to-first (zigzag L2 reuse across launches)
+  int polite;                           // producers / epilogue warps sleep between barrier polls
   int debug; long long* dbg;            // BIN_B200_DEBUG=8: block 0 records clock64 at role milestones (tools only)
 };
 // timeline layout (bin_debug_timeline): [role][iter][4]; role 0 = producer (k 0,1 per stage) and epilogue B (k 2,3 per tile),
@@ -177,7 +178,8 @@ __global__ void __launch_bounds__(QUADT ? 448 : 384, 1) rdb_tail_kernel(const __
         const uint32_t slot = STREAMS ? Y + 2 * (k & 1) : k % kRtStages;
         const uint32_t par = STREAMS ? (k >> 1) & 1 : (k / kRtStages) & 1;
         if (Y == 0) rt_rec(p, 0, k, 0);
-        mbar_wait(&ctrl->empty[slot], par ^ 1);
+        if (p.polite) mbar_wait_polite(&ctrl->empty[slot], par ^ 1, 200);
+        else mbar_wait(&ctrl->empty[slot], par ^ 1);
         if (Y == 0) rt_rec(p, 0, k, 1);
         mbar_expect_tx(&ctrl->full[slot], kRtABytes);
         const bool seg1 = c >= 3;
@@ -447,7 +449,8 @@ __global__ void __launch_bounds__(QUADT ? 448 : 384, 1) rdb_tail_kernel(const __
         rbuf[k] = valid ? *reinterpret_cast<const uint4*>(p.res + off) : make_uint4(0, 0, 0, 0);
       }
       if (warp == 8 && lane == 0) rt_rec(p, 0, tl, 2);
-      mbar_wait(&ctrl->lff_full[lb], (tl / 3) & 1);
+      if (p.polite) mbar_wait_polite(&ctrl->lff_full[lb], (tl / 3) & 1, 40);
+      else mbar_wait(&ctrl->lff_full[lb], (tl / 3) & 1);
       if (warp == 8 && lane == 0) rt_rec(p, 0, tl, 3);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kRtLffCol0 + lb * kRtN;
@@ -832,6 +835,7 @@ int launch_rdb_tail(const bin_act_t& x, int x_plane0, const bin_act_t& g, int g_
   p.out = reinterpret_cast<__half*>(out.ptr); p.out_planes = out.planes; p.out_plane0 = out_plane0;
   p.res = reinterpret_cast<const __half*>(x.ptr); p.res_planes = x.planes; p.res_plane0 = x_plane0;
   p.reverse = reverse ? 1 : 0;
+  p.polite = options().polite ? 1 : 0;
   const bool streams = options().tail_streams;
   p.debug = options().debug;
 #ifdef BIN_B200_TOOLS
