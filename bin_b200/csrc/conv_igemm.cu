@@ -88,6 +88,15 @@ __device__ __forceinline__ void dbg_rec(const ConvParams& p, int role, uint32_t 
 #endif
 }
 
+// tools build: which epilogue warp the timeline records (BIN_B200_DEBUG bits 12..14 -> warps 4..11)
+__device__ __forceinline__ int kDbgEpiWarp(const ConvParams& p) {
+#ifdef BIN_B200_TOOLS
+  return 4 + ((p.debug >> 12) & 7);
+#else
+  return 4;
+#endif
+}
+
 constexpr int kThreads = 384;   // 12 warps, see the role table below
 
 // Warp roles (384 threads, 1 CTA/SM, persistent over tiles).  Measured on B200: one mbarrier poll
@@ -164,6 +173,9 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
   float* sbias = reinterpret_cast<float*>(smem + 1024);
 
   const int warp = threadIdx.x >> 5;
+  // Role index.  QUAD + p.spread: the fourth MMA warp swaps places with producer B (physical warp 2 <-> 13), so that the four
+  // MMA issuers sit on four different SM sub-partitions (warp % 4) instead of two of them sharing sub-partition 1.
+  const int rw = (QUAD && p.spread) ? (warp == 2 ? 13 : (warp == 13 ? 2 : warp)) : warp;
   const int lane = threadIdx.x & 31;
   const uint32_t S = p.nstages;
   const int nchunks = p.nch0 + p.nch1;
@@ -200,7 +212,7 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
   if (bias_in_smem)
     for (int i = threadIdx.x; i < NT * p.nh; i += blockDim.x) sbias[i] = p.bias[i];
   const float* bsrc = bias_in_smem ? sbias : p.bias;
-  if (warp == 2) {
+  if (rw == 2) {
     if constexpr (PAIR) { tmem_alloc_pair(&ctrl->tmem_base, C::TMEM_COLS); tmem_relinquish_pair(); }
     else { tmem_alloc(&ctrl->tmem_base, C::TMEM_COLS); tmem_relinquish(); }
   }
@@ -210,9 +222,9 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
 
-  if ((warp == 0 || warp == 2) && lane == 0) {
+  if ((rw == 0 || rw == 2) && lane == 0) {
     // ========================================================== TMA producers (stage i -> producer i%2)
-    const uint32_t Y = warp >> 1;
+    const uint32_t Y = rw >> 1;
     if (p.resident && Y == 0) {
       for (int c = 0; c < nchunks; ++c) {
         mbar_expect_tx(&ctrl->wfull[c], C::W_CHUNK / WH);
@@ -272,14 +284,14 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
         if (++s == S) { s = 0; ph ^= 1; }
       }
     }
-  } else if (PAIR && warp == 1 && rank == 1) {
+  } else if (PAIR && rw == 1 && rank == 1) {
     // ========================================================== peer: tell the leader when this CTA's B halves have landed
     for (int c = 0; c < nchunks; ++c) mbar_wait(&ctrl->wfull[c], 0);
     if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctrl->wready), 0));
-  } else if ((warp == 1 || warp == 3 || (QUAD && warp >= 12)) && rank == 0) {
+  } else if ((rw == 1 || rw == 3 || (QUAD && rw >= 12)) && rank == 0) {
     // ========================================================== MMA issuers (warp converged, one elected lane; PAIR: leader only)
-    const uint32_t Y = QUAD ? ((warp == 1 || warp == 12) ? 0u : 1u) : (uint32_t)(warp >> 1);   // stage parity this warp issues
-    const uint32_t mq = (QUAD && warp >= 12) ? 1u : 0u;                                        // QUAD: its accumulator
+    const uint32_t Y = QUAD ? ((rw == 1 || rw == 12) ? 0u : 1u) : (uint32_t)(rw >> 1);   // stage parity this warp issues
+    const uint32_t mq = (QUAD && rw >= 12) ? 1u : 0u;                                        // QUAD: its accumulator
     constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 256 : 128, C::NMMA);
     constexpr uint32_t D_HI = (128u >> 4) | (1u << 14);            // SBO=128 B, descriptor version 1
     constexpr uint32_t A_LBO = ((uint32_t)C::A_PLANE >> 4) << 16;
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
         //    (no hand-off, no shared counter); a stage is recycled when both have committed (empty count 2), so neither
         //    waiter can be lapped.  The per-accumulator MMA order is unchanged -> bit-identical results.
         const bool mine = (!QUAD && p.msplit) ? true : (it & 1u) == Y;
-        if (mine && warp == 1 && lane == 0) dbg_rec(p, 1, dbg_it, 0);
+        if (mine && rw == 1 && lane == 0) dbg_rec(p, 1, dbg_it, 0);
         if (mine) {
           // Each MMA warp waits ONLY on the stages it issues (S is even, so stage parity = warp): a parity-tracked
           // mbarrier must never be waited on by a thread that can fall a whole phase behind -- mbarrier.try_wait may
@@ -319,7 +331,7 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
           if (QUAD || !p.msplit)
             while (ctrl->issued[mq] < it) __nanosleep(32);  // stage it-1 fully issued by the other warp (a tight
                                                             // shared-memory spin would compete with the MMA operand fetch)
-          if (warp == 1 && lane == 0) dbg_rec(p, 1, dbg_it, 1);
+          if (rw == 1 && lane == 0) dbg_rec(p, 1, dbg_it, 1);
           tc_fence_after();
           const uint32_t st_base = smem_u32(stage0 + (size_t)s * stage_bytes);
           for (int u = 0; u < nu; ++u) {
@@ -360,7 +372,7 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
           tc_fence_before();                               // order this warp's tcgen05.mma before the flag (the
           __syncwarp();                                    // other warp pairs it with tc_fence_after above)
           if (lane == 0 && (QUAD || !p.msplit)) ctrl->issued[mq] = it + 1;   // hand over to the warp of the other stage parity
-          if (warp == 1 && lane == 0) dbg_rec(p, 1, dbg_it, 2);
+          if (rw == 1 && lane == 0) dbg_rec(p, 1, dbg_it, 2);
           ++dbg_it;
         }
         unit += nu;
@@ -465,10 +477,10 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
         }
       }
       constexpr float kAcc = X3 ? (1.f / 256.f) : 1.f;      // X3 weights are packed scaled by 2^8
-      if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 0);
+      if (warp == kDbgEpiWarp(p) && lane == 0) dbg_rec(p, 2, acc_it, 0);
       if (p.polite) mbar_wait_polite(&ctrl->tmem_full[as], aph, 40, kTag | (4ull << 32) | acc_it);
       else mbar_wait(&ctrl->tmem_full[as], aph, kTag | (4ull << 32) | acc_it);
-      if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 1);
+      if (warp == kDbgEpiWarp(p) && lane == 0) dbg_rec(p, 2, acc_it, 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + m * C::NMMA;
       if constexpr (EPI == BIN_EPI_P8) {
@@ -498,7 +510,7 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
             }
           }
           tmem_ld_wait();
-          if (warp == 4 && lane == 0 && g0 == 0) dbg_rec(p, 2, acc_it, 3);        // tools build: TMEM loads have landed
+          if (warp == kDbgEpiWarp(p) && lane == 0 && g0 == 0) dbg_rec(p, 2, acc_it, 3);        // tools build: TMEM loads have landed
 #pragma unroll
           for (int j = 0; j < GRP / 16; ++j) {
             const int n0 = g0 + 16 * j;
@@ -637,7 +649,7 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
         if constexpr (PAIR) mbar_arrive_cluster(tempty0 + as * 8);
         else mbar_arrive(&ctrl->tmem_empty[as]);
       }
-      if (warp == 4 && lane == 0) dbg_rec(p, 2, acc_it, 2);
+      if (warp == kDbgEpiWarp(p) && lane == 0) dbg_rec(p, 2, acc_it, 2);
     }
   }
 
@@ -645,7 +657,7 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
   tc_fence_before();
   __syncthreads();
   if constexpr (PAIR) cluster_sync_all();                      // the leader's MMAs touch the peer's smem / TMEM
-  if (warp == 2) {
+  if (rw == 2) {
     tc_fence_after();
     if constexpr (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
     else tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -764,6 +776,7 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
   p.debug = options().debug;
   p.msplit = options().msplit ? 1 : 0;
   p.polite = options().polite ? 1 : 0;
+  p.spread = options().spread ? 1 : 0;
   p.reverse = (reverse && EPI == BIN_EPI_P8) ? 1 : 0;     // (the FINAL epilogue prefetches tile + gridDim.x: forward only)
 #ifdef BIN_B200_TOOLS
   if (p.debug & 8) {
