@@ -365,28 +365,6 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
             }
             __syncwarp();
           }
-          if constexpr (SX && EPI == BIN_EPI_P8 && !PAIR) {
-            // x-stack sum on the tensor pipe: out[p] = D[p][kx=0] + D[p+1][kx=1] + D[p+2][kx=2].  After the tile's last MMAs
-            // column group kx of the accumulator is shifted down kx lanes (tcgen05.shift moves 8 columns by one lane inside
-            // every 32-lane group = one 32-pixel tile row), so the epilogue adds three column groups of its OWN lane instead
-            // of fetching 64 values per thread from lanes +1 / +2 with SHFL -- the shuffles shared the SM's shared-memory
-            // crossbar with the operand fetch of the MMAs (7 KB per 128x96x16 MMA = 56 cycles at 128 B/clk), which is what
-            // bounds this kernel.  Issued by the warp that issued the accumulator's last MMAs, in order behind them.
-            if (p.shift && j == spt - 1 && elect_one()) {
-#pragma unroll
-              for (int m = 0; m < kMT; ++m) {
-                if (QUAD ? (uint32_t)m != mq : (p.msplit && (uint32_t)m != Y)) continue;
-                const uint32_t d = tmem_base + as * C::ACC_COLS + m * C::NMMA;
-#pragma unroll
-                for (int kx = 1; kx < 3; ++kx)
-#pragma unroll
-                  for (int r = 0; r < kx; ++r)
-#pragma unroll
-                    for (int c8 = 0; c8 < NT; c8 += 8) tmem_shift_down(d + kx * NT + c8);
-              }
-            }
-            __syncwarp();
-          }
           if (elect_one()) {                               // frees the smem stage (in both CTAs) once these MMAs retire
             if constexpr (PAIR) umma_commit_pair(&ctrl->empty[s]);
             else umma_commit(&ctrl->empty[s]);
@@ -512,7 +490,6 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
 #pragma unroll
         for (int g0 = 0; g0 < NT; g0 += GRP) {
           uint32_t v[(SX ? 3 : 1) * GRP];
-          const bool shifted = SX && !PAIR && p.shift;     // the kx column groups were already shifted in TMEM (see the MMA warps)
 #ifdef BIN_B200_TOOLS      // epilogue ablations for the timeline tool (timing only, results are garbage): BIN_B200_DEBUG bits 5..8
           const bool abl_ld = p.debug & 32, abl_bias = p.debug & 64, abl_shfl = p.debug & 128, abl_st = p.debug & 256;
           if (abl_ld) {
@@ -542,8 +519,8 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
               // out[p] = D[p][kx=0] + D[p+1][kx=1] + D[p+2][kx=2]; p+1, p+2 are lanes +1, +2 of this warp
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float b1 = (abl_shfl || shifted) ? __uint_as_float(v[GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[GRP + 16 * j + i]), 1);
-                const float b2 = (abl_shfl || shifted) ? __uint_as_float(v[2 * GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[2 * GRP + 16 * j + i]), 2);
+                const float b1 = abl_shfl ? __uint_as_float(v[GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[GRP + 16 * j + i]), 1);
+                const float b2 = abl_shfl ? __uint_as_float(v[2 * GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[2 * GRP + 16 * j + i]), 2);
                 f[i] = ((__uint_as_float(v[16 * j + i]) + b1) + b2) * kAcc + (abl_bias ? 0.25f : sbias[n0 + i]);
               }
             } else {
@@ -800,7 +777,6 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
   p.msplit = options().msplit ? 1 : 0;
   p.polite = options().polite ? 1 : 0;
   p.spread = options().spread ? 1 : 0;
-  p.shift = options().shift ? 1 : 0;
   p.reverse = (reverse && EPI == BIN_EPI_P8) ? 1 : 0;     // (the FINAL epilogue prefetches tile + gridDim.x: forward only)
 #ifdef BIN_B200_TOOLS
   if (p.debug & 8) {

@@ -297,7 +297,7 @@ def test_cta_pair_kernels_bit_identical_to_single_cta():
     """The cta_group::2 kernels (rdb_tail_pair_kernel, conv_igemm_kernel<...,PAIR>) and the M-split MMA-warp scheme of the
     conv kernel keep the per-accumulator MMA order of the default kernels: a whole window must hash identically under
     every combination of BIN_B200_PAIR / BIN_B200_MSPLIT / BIN_B200_QUAD (four MMA warps) / BIN_B200_ZIGZAG (reversed tile
-    order of alternate launches) / BIN_B200_SHIFT (x-stack sum by tcgen05.shift) / SPREAD / POLITE; the
+    order of alternate launches) / BIN_B200_SPREAD / BIN_B200_POLITE; the
     library reads the switches once per process, hence children.  Shapes: odd tile counts (dummy peer tile), many tiles per cluster."""
     import subprocess
     import sys
@@ -314,15 +314,13 @@ def test_cta_pair_kernels_bit_identical_to_single_cta():
         "print('HASH', h.hexdigest())\n" % ROOT)
     got = {}
     base = {"BIN_B200_PAIR": "0", "BIN_B200_MSPLIT": "0", "BIN_B200_QUAD": "0", "BIN_B200_ZIGZAG": "0", "BIN_B200_TAILQ": "0",
-            "BIN_B200_SHIFT": "0", "BIN_B200_SPREAD": "0", "BIN_B200_POLITE": "0"}
-    sh = {"BIN_B200_SHIFT": "1"}                      # x-stack sum by tcgen05.shift in TMEM instead of SHFL in the epilogue
+            "BIN_B200_SPREAD": "0", "BIN_B200_POLITE": "0"}
     for tag, over in (("two-warp", {}), ("quad", {"BIN_B200_QUAD": "1"}), ("quad+tailq", {"BIN_B200_QUAD": "1", "BIN_B200_TAILQ": "1"}),
                       ("tailq", {"BIN_B200_TAILQ": "1"}), ("pair", {"BIN_B200_PAIR": "1"}),
                       ("msplit", {"BIN_B200_MSPLIT": "1"}), ("pair+msplit", {"BIN_B200_PAIR": "1", "BIN_B200_MSPLIT": "1"}),
                       ("quad+zigzag", {"BIN_B200_QUAD": "1", "BIN_B200_ZIGZAG": "1"}), ("pair+zigzag", {"BIN_B200_PAIR": "1", "BIN_B200_ZIGZAG": "1"}),
-                      ("shift", sh), ("quad+shift", dict(sh, BIN_B200_QUAD="1")), ("msplit+shift", dict(sh, BIN_B200_MSPLIT="1")),
-                      ("quad+tailq+shift+spread+polite", dict(sh, BIN_B200_QUAD="1", BIN_B200_TAILQ="1", BIN_B200_SPREAD="1", BIN_B200_POLITE="1")),
-                      ("pair+shift", dict(sh, BIN_B200_PAIR="1"))):
+                      ("quad+tailq+spread+polite", {"BIN_B200_QUAD": "1", "BIN_B200_TAILQ": "1", "BIN_B200_SPREAD": "1", "BIN_B200_POLITE": "1"}),
+                      ("spread+polite", {"BIN_B200_SPREAD": "1", "BIN_B200_POLITE": "1"})):
         env = dict(base, **over)
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, (tag, r.stderr[-2000:])
