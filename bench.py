@@ -312,7 +312,13 @@ def dominant_kernel_roofline(torch, ops, pk, ncalls, h, w):
     return {"bound": "tensor", "kernel": "RDB 3x3 convs 0..2, x-stacked implicit GEMM (3 shapes)", "achieved": ach,
             "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({pk['source']}, burst: kernel timed alone)",
-            "algorithmic_flops_per_launch_set": tot_flops, "ms_per_launch_set": tot_ms, "second_kernel": tail,
+            "algorithmic_flops_per_launch_set": tot_flops, "ms_per_launch_set": tot_ms,
+            # every 128x96x16 MMA fetches A (4 KB) + B (3 KB) from shared memory at 128 B/clk = 56 cycles against
+            # 48 cycles of tensor time, so this formulation tops out at 0.857 of the tensor peak before TMA fill / epilogue
+            "on_chip_limit": {"resource": "shared-memory operand port", "bytes_per_mma": 7168, "port_cycles_per_mma": 56,
+                              "tensor_cycles_per_mma": 48, "ceiling_frac_of_peak": 48.0 / 56.0,
+                              "frac_of_ceiling": ach / peak / (48.0 / 56.0)},
+            "second_kernel": tail,
             "memory_bound_kernels": mem}
 
 
