@@ -101,9 +101,9 @@ if tag == "r01":
          "Algorithmic FLOPs per launch: 2*5*230400*(192*32*9 + 224*96).")
 
 if tag == "r02":
-    launches("r02p_launches_window.csv", "r02_launches_window.md",
+    launches("r02z_launches_window.csv", "r02_launches_window.md",
              "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 227 -c 223 --csv python tools/run_window.py 2` "
-             "(BIN_B200_GRAPH=0; skip = 4 batched weight-pack launches + the 223 launches of window 0; CTA-pair kernels on).")
+             "(BIN_B200_GRAPH=0; skip = 4 batched weight-pack launches + the 223 launches of window 0; default switches: four MMA warps, single-CTA kernels; final tree of round 2).")
     FP = [("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe % of peak"),
           ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots active %"),
           ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts")]
