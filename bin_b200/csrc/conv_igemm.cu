@@ -261,6 +261,14 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
           else mbar_wait(&ctrl->empty[s], ph ^ 1, kTag | (1ull << 32) | it);
           if (Y == 0) dbg_rec(p, 0, it >> 1, 1);
           uint8_t* dst = stage0 + (size_t)s * stage_bytes;
+#ifdef BIN_B200_TOOLS      // ablation (timing only): no global -> shared input traffic at all = what ANY fusion that keeps the
+          if (!PAIR && p.resident && (p.debug & 1024)) {   // inputs on chip could at best save (BIN_B200_DEBUG bit 10)
+            mbar_arrive(&ctrl->full[s]);
+            unit += nu;
+            if (++s == S) { s = 0; ph ^= 1; }
+            continue;
+          }
+#endif
           if (!PAIR || rank == 0) mbar_expect_tx(&ctrl->full[s], (uint32_t)((PAIR ? 2 : 1) * nu * unit_bytes));
           for (int u = 0; u < nu; ++u) {
             const int c = (unit + u) / C::NSUB, sub = (unit + u) % C::NSUB;
