@@ -147,9 +147,15 @@ __device__ __forceinline__ void split_store(__half* base_hi, __half* base_lo, co
 // scheme do.  The role timelines show a single issuing warp sustaining one MMA per ~82 cycles while two warps issuing
 // CONCURRENTLY reach the isolated rate (57); with four warps two are always issuing (one per accumulator) while the other
 // two wait on their next barrier.  The MMA order per accumulator is unchanged -> bit-identical results.
-template <int NT, int KS, int EPI, bool SX, bool X3, bool PAIR = false, bool QUAD = false>
-__global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+// EPI2 (on top of QUAD, x-stacked fp16 conv only; 704 threads): TWO sets of eight epilogue warps, set e owns accumulator
+// stage e, i.e. every second tile of the CTA.  The epilogue of one tile is a 3 000-cycle dependent chain (barrier wait,
+// TMEM loads, 64 SHFL, stores, arrive) whatever its instruction count, and with one set of warps doing EVERY tile that chain
+// was the tile period (the MMAs of a 96-channel tile need ~2 000 cycles of operand-port time).  Two sets halve the rate each
+// set has to sustain; under the 704-thread register bound (88) a warp walks its 32 output channels in two passes of 16.
+template <int NT, int KS, int EPI, bool SX, bool X3, bool PAIR = false, bool QUAD = false, bool EPI2 = false>
+__global__ void __launch_bounds__(EPI2 ? kThreads + 64 + 256 : (QUAD ? kThreads + 64 : kThreads), 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using C = ConvCfg<NT, KS, SX>;
+  static_assert(!EPI2 || (QUAD && SX && EPI == BIN_EPI_P8), "two epilogue sets exist for the four-MMA-warp x-stacked conv");
   static_assert(!PAIR || (SX && !X3 && EPI == BIN_EPI_P8), "the CTA-pair form exists for the x-stacked fp16 convs");
   static_assert(!QUAD || (!X3 && !PAIR && EPI != BIN_EPI_FINAL), "the four-MMA-warp form exists for the fp16 P8 / PixelShuffle convs");
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -296,7 +302,7 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
     // ========================================================== peer: tell the leader when this CTA's B halves have landed
     for (int c = 0; c < nchunks; ++c) mbar_wait(&ctrl->wfull[c], 0);
     if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctrl->wready), 0));
-  } else if ((rw == 1 || rw == 3 || (QUAD && rw >= 12)) && rank == 0) {
+  } else if ((rw == 1 || rw == 3 || (QUAD && (rw == 12 || rw == 13))) && rank == 0) {
     // ========================================================== MMA issuers (warp converged, one elected lane; PAIR: leader only)
     const uint32_t Y = QUAD ? ((rw == 1 || rw == 12) ? 0u : 1u) : (uint32_t)(rw >> 1);   // stage parity this warp issues
     const uint32_t mq = (QUAD && rw >= 12) ? 1u : 0u;                                        // QUAD: its accumulator
@@ -392,11 +398,13 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
       }
       __syncwarp();
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if ((warp >= 4 && warp < 12) || (EPI2 && warp >= 14)) {
     // ========================================================== epilogue
-    const int q = warp & 3;
-    const int m = (warp - 4) >> 2;                      // which 128-row accumulator of the tile
-    uint32_t acc_it = 0;
+    const int eset = (EPI2 && warp >= 14) ? 1 : 0;      // EPI2: which set = which accumulator stage = tile parity
+    const int q = warp & 3;                             // TMEM lane quarter (fixed by the hardware: warp % 4)
+    const int m = ((eset ? warp - 14 : warp - 4) >> 2); // which 128-row accumulator of the tile
+    const int etq0 = tq0 + eset * tqstep, etqstep = EPI2 ? 2 * tqstep : tqstep;
+    uint32_t acc_it = (uint32_t)eset;
     // FINAL epilogue: the mean of the input frames (RDN.py:221/279/333) of tile t+1 is loaded while tile t is being
     // processed (one tile of software pipelining: a cold DRAM round trip per tile was the kernel's critical path).
     constexpr int NFV = (EPI == BIN_EPI_FINAL) ? 3 * BIN_MAX_FRAMES : 1;
@@ -429,12 +437,12 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
     constexpr bool kIncr = !PAIR;
     int c_nh = 0, c_tx = 0, c_ty = 0, c_b = 0, d_nh = 0, d_tx = 0, d_ty = 0, d_b = 0;
     if (kIncr && !p.reverse) {
-      int t = tq0;
+      int t = etq0;
       c_nh = t % p.nh; t /= p.nh; c_tx = t % p.tiles_x; t /= p.tiles_x; c_ty = t % p.tiles_y; c_b = t / p.tiles_y;
-      t = tqstep;
+      t = etqstep;
       d_nh = t % p.nh; t /= p.nh; d_tx = t % p.tiles_x; t /= p.tiles_x; d_ty = t % p.tiles_y; d_b = t / p.tiles_y;
     }
-    for (int tq = tq0; tq < tqn; tq += tqstep, ++acc_it) {
+    for (int tq = etq0; tq < tqn; tq += etqstep, acc_it += (EPI2 ? 2u : 1u)) {
       bool live = true;
       int tile, nh, txi, tyi, b;
       if (kIncr && !p.reverse) {
@@ -494,7 +502,7 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
       if constexpr (EPI == BIN_EPI_P8) {
         // TMEM loads are issued in batches (tcgen05.wait::ld waits for ALL outstanding loads, so one wait per
         // 16 columns serialised a ~200-cycle round trip six times per tile and made the LFF epilogue the bottleneck)
-        constexpr int GRP = SX ? 32 : (NT % 48 == 0 ? 48 : (NT % 32 == 0 ? 32 : 16));   // output channels per batch
+        constexpr int GRP = SX ? (EPI2 ? 16 : 32) : (NT % 48 == 0 ? 48 : (NT % 32 == 0 ? 32 : 16));   // output channels per batch
 #pragma unroll
         for (int g0 = 0; g0 < NT; g0 += GRP) {
           uint32_t v[(SX ? 3 : 1) * GRP];
@@ -818,6 +826,18 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
     // (not with a residual / accumulate epilogue: its prefetch registers do not fit under the 448-thread bound without
     // spills, and the data-gradient convs of the training step measured 1.5 % slower with it)
     if (options().quad && (SX || a.res.ptr == nullptr)) {
+      if constexpr (SX && EPI == BIN_EPI_P8) {
+        if (options().epi2) {
+          auto k2 = conv_igemm_kernel<NT, KS, EPI, SX, X3, false, true, true>;
+          static std::atomic<unsigned long long> epi2_opted{0};
+          BIN_TRY(ensure_dynamic_smem(k2, kSmemMax, epi2_opted));
+          const int g2 = p.ntiles < num_sms() ? p.ntiles : num_sms();
+          if (g2 < 1) return BIN_OK;
+          k2<<<g2, kThreads + 64 + 256, smem_bytes, s>>>(p);
+          BIN_CUDA_OK(cudaGetLastError());
+          return BIN_OK;
+        }
+      }
       auto kq = conv_igemm_kernel<NT, KS, EPI, SX, X3, false, true>;
       static std::atomic<unsigned long long> quad_opted{0};   // per instantiation, per device
       BIN_TRY(ensure_dynamic_smem(kq, kSmemMax, quad_opted));

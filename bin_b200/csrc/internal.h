@@ -52,6 +52,7 @@ struct Options {
   bool msplit;               // BIN_B200_MSPLIT: conv MMA warps split the tile's two accumulators instead of alternating stages
   bool quad;                 // BIN_B200_QUAD=0 falls back to two MMA warps in the x-stacked conv kernel (default: four)
   bool tailq;                // BIN_B200_TAILQ: two MMA warps per tile stream in rdb_tail_kernel (448 threads)
+  bool epi2;                 // BIN_B200_EPI2: two alternating sets of epilogue warps in the x-stacked conv (704 threads)
   bool spread;               // BIN_B200_SPREAD: QUAD convs put one MMA warp on each SM sub-partition
   bool polite;               // BIN_B200_POLITE: producers / epilogue warps sleep between barrier polls (power)
   bool zigzag;               // BIN_B200_ZIGZAG: consecutive RDB launches walk the tiles in opposite directions (L2 reuse)
