@@ -65,6 +65,7 @@ struct Ctrl {
   uint64_t wfull[kMaxResidentChunks];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t shifted[4];        // EPI2 + shift: [stage * 2 + m] the x-stack column groups of that accumulator have been shifted
   uint64_t wready;            // PAIR: the peer's resident weight halves have landed (leader's copy is used)
   uint32_t tmem_base;
   volatile uint32_t issued[2];   // per accumulator (QUAD) / [0] only: number of pipeline stages whose MMAs have been issued (hand-off)
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(EPI2 ? kThreads + 64 + 256 : (QUAD ? kThreads 
       mbar_init(&ctrl->empty[i], (QUAD || p.msplit) ? 2 : 1);   // M-split / QUAD: two MMA warps consume every stage
     }
     for (int i = 0; i < kMaxResidentChunks; ++i) mbar_init(&ctrl->wfull[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&ctrl->shifted[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctrl->tmem_full[i], QUAD ? 4 : 2);        // one tcgen05.commit per MMA warp
       mbar_init(&ctrl->tmem_empty[i], PAIR ? 16 : 8);      // ONE arrival per epilogue warp (of both CTAs): 256 threads
@@ -499,6 +501,30 @@ __global__ void __launch_bounds__(EPI2 ? kThreads + 64 + 256 : (QUAD ? kThreads 
       if (warp == kDbgEpiWarp(p) && lane == 0) dbg_rec(p, 2, acc_it, 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + m * C::NMMA;
+      bool shifted = false;
+      if constexpr (EPI2) {
+        // x-stack sum in TMEM: column group kx of the finished accumulator is shifted down kx lanes by the tensor pipe
+        // (tcgen05.shift works inside each 32-lane group = one 32-pixel tile row), so the three groups are added lane-wise
+        // below and the 64 SHFL per thread -- which cross the same shared-memory crossbar as the MMA operand fetch, the
+        // resource that bounds this kernel -- disappear.  Issued by one thread per accumulator AFTER tmem_full (a shift is
+        // not ordered behind MMAs to the same columns), its latency is affordable because this set has two tile periods.
+        if (p.shift) {
+          shifted = true;
+          if (q == 0 && elect_one()) {
+            const uint32_t d = tmem_base + as * C::ACC_COLS + m * C::NMMA;
+#pragma unroll
+            for (int kx = 1; kx < 3; ++kx)
+#pragma unroll
+              for (int r = 0; r < kx; ++r)
+#pragma unroll
+                for (int c8 = 0; c8 < NT; c8 += 8) tmem_shift_down(d + kx * NT + c8);
+            umma_commit(&ctrl->shifted[as * 2 + m]);
+          }
+          __syncwarp();
+          mbar_wait(&ctrl->shifted[as * 2 + m], aph, kTag | (5ull << 32) | acc_it);
+          tc_fence_after();
+        }
+      }
       if constexpr (EPI == BIN_EPI_P8) {
         // TMEM loads are issued in batches (tcgen05.wait::ld waits for ALL outstanding loads, so one wait per
         // 16 columns serialised a ~200-cycle round trip six times per tile and made the LFF epilogue the bottleneck)
@@ -535,8 +561,8 @@ __global__ void __launch_bounds__(EPI2 ? kThreads + 64 + 256 : (QUAD ? kThreads 
               // out[p] = D[p][kx=0] + D[p+1][kx=1] + D[p+2][kx=2]; p+1, p+2 are lanes +1, +2 of this warp
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float b1 = abl_shfl ? __uint_as_float(v[GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[GRP + 16 * j + i]), 1);
-                const float b2 = abl_shfl ? __uint_as_float(v[2 * GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[2 * GRP + 16 * j + i]), 2);
+                const float b1 = (abl_shfl || shifted) ? __uint_as_float(v[GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[GRP + 16 * j + i]), 1);
+                const float b2 = (abl_shfl || shifted) ? __uint_as_float(v[2 * GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[2 * GRP + 16 * j + i]), 2);
                 f[i] = ((__uint_as_float(v[16 * j + i]) + b1) + b2) * kAcc + (abl_bias ? 0.25f : sbias[n0 + i]);
               }
             } else {
@@ -793,6 +819,7 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
   p.msplit = options().msplit ? 1 : 0;
   p.polite = options().polite ? 1 : 0;
   p.spread = options().spread ? 1 : 0;
+  p.shift = options().shift ? 1 : 0;
   p.reverse = (reverse && EPI == BIN_EPI_P8) ? 1 : 0;     // (the FINAL epilogue prefetches tile + gridDim.x: forward only)
 #ifdef BIN_B200_TOOLS
   if (p.debug & 8) {
