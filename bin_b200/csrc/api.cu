@@ -29,8 +29,6 @@ static Options read_options() {
   o.msplit = (e = env("BIN_B200_MSPLIT")) && *e == '1';
   o.quad = !((e = env("BIN_B200_QUAD")) && *e == '0');  // four MMA warps in the x-stacked conv: default (measured +8 %)
   o.tailq = (e = env("BIN_B200_TAILQ")) && *e == '1';
-  o.shift = (e = env("BIN_B200_SHIFT")) && *e == '1';
-  o.epi2 = (e = env("BIN_B200_EPI2")) && *e == '1';
   o.spread = (e = env("BIN_B200_SPREAD")) && *e == '1';
   o.polite = (e = env("BIN_B200_POLITE")) && *e == '1';
   o.zigzag = (e = env("BIN_B200_ZIGZAG")) && *e == '1';

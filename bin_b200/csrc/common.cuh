@@ -156,13 +156,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-// Shift 8 consecutive 32-bit TMEM columns down by one lane, independently inside each group of 32 lanes: lane i <- lane i+1
-// for i % 32 < 31, lane 31 of each group keeps its value (measured with tools/shift_probe.cu; the column need not be
-// 8-aligned, the lane field of taddr is ignored).  Asynchronous on the tensor pipe, tracked by tcgen05.commit.  NOT ordered
-// behind earlier tcgen05.mma to the same columns: issue it only after the accumulator's commit has been observed.
-__device__ __forceinline__ void tmem_shift_down(uint32_t taddr) {
-  asm volatile("tcgen05.shift.cta_group::1.down [%0];" ::"r"(taddr) : "memory");
-}
 // TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(

@@ -65,7 +65,6 @@ struct Ctrl {
   uint64_t wfull[kMaxResidentChunks];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t shifted[4];        // EPI2 + shift: [stage * 2 + m] the x-stack column groups of that accumulator have been shifted
   uint64_t wready;            // PAIR: the peer's resident weight halves have landed (leader's copy is used)
   uint32_t tmem_base;
   volatile uint32_t issued[2];   // per accumulator (QUAD) / [0] only: number of pipeline stages whose MMAs have been issued (hand-off)
@@ -148,15 +147,9 @@ __device__ __forceinline__ void split_store(__half* base_hi, __half* base_lo, co
 // scheme do.  The role timelines show a single issuing warp sustaining one MMA per ~82 cycles while two warps issuing
 // CONCURRENTLY reach the isolated rate (57); with four warps two are always issuing (one per accumulator) while the other
 // two wait on their next barrier.  The MMA order per accumulator is unchanged -> bit-identical results.
-// EPI2 (on top of QUAD, x-stacked fp16 conv only; 704 threads): TWO sets of eight epilogue warps, set e owns accumulator
-// stage e, i.e. every second tile of the CTA.  The epilogue of one tile is a 3 000-cycle dependent chain (barrier wait,
-// TMEM loads, 64 SHFL, stores, arrive) whatever its instruction count, and with one set of warps doing EVERY tile that chain
-// was the tile period (the MMAs of a 96-channel tile need ~2 000 cycles of operand-port time).  Two sets halve the rate each
-// set has to sustain; under the 704-thread register bound (88) a warp walks its 32 output channels in two passes of 16.
-template <int NT, int KS, int EPI, bool SX, bool X3, bool PAIR = false, bool QUAD = false, bool EPI2 = false>
-__global__ void __launch_bounds__(EPI2 ? kThreads + 64 + 256 : (QUAD ? kThreads + 64 : kThreads), 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+template <int NT, int KS, int EPI, bool SX, bool X3, bool PAIR = false, bool QUAD = false>
+__global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using C = ConvCfg<NT, KS, SX>;
-  static_assert(!EPI2 || (QUAD && SX && EPI == BIN_EPI_P8), "two epilogue sets exist for the four-MMA-warp x-stacked conv");
   static_assert(!PAIR || (SX && !X3 && EPI == BIN_EPI_P8), "the CTA-pair form exists for the x-stacked fp16 convs");
   static_assert(!QUAD || (!X3 && !PAIR && EPI != BIN_EPI_FINAL), "the four-MMA-warp form exists for the fp16 P8 / PixelShuffle convs");
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -205,7 +198,6 @@ __global__ void __launch_bounds__(EPI2 ? kThreads + 64 + 256 : (QUAD ? kThreads 
       mbar_init(&ctrl->empty[i], (QUAD || p.msplit) ? 2 : 1);   // M-split / QUAD: two MMA warps consume every stage
     }
     for (int i = 0; i < kMaxResidentChunks; ++i) mbar_init(&ctrl->wfull[i], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&ctrl->shifted[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctrl->tmem_full[i], QUAD ? 4 : 2);        // one tcgen05.commit per MMA warp
       mbar_init(&ctrl->tmem_empty[i], PAIR ? 16 : 8);      // ONE arrival per epilogue warp (of both CTAs): 256 threads
@@ -304,7 +296,7 @@ __global__ void __launch_bounds__(EPI2 ? kThreads + 64 + 256 : (QUAD ? kThreads 
     // ========================================================== peer: tell the leader when this CTA's B halves have landed
     for (int c = 0; c < nchunks; ++c) mbar_wait(&ctrl->wfull[c], 0);
     if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctrl->wready), 0));
-  } else if ((rw == 1 || rw == 3 || (QUAD && (rw == 12 || rw == 13))) && rank == 0) {
+  } else if ((rw == 1 || rw == 3 || (QUAD && rw >= 12)) && rank == 0) {
     // ========================================================== MMA issuers (warp converged, one elected lane; PAIR: leader only)
     const uint32_t Y = QUAD ? ((rw == 1 || rw == 12) ? 0u : 1u) : (uint32_t)(rw >> 1);   // stage parity this warp issues
     const uint32_t mq = (QUAD && rw >= 12) ? 1u : 0u;                                        // QUAD: its accumulator
@@ -400,13 +392,11 @@ __global__ void __launch_bounds__(EPI2 ? kThreads + 64 + 256 : (QUAD ? kThreads 
       }
       __syncwarp();
     }
-  } else if ((warp >= 4 && warp < 12) || (EPI2 && warp >= 14)) {
+  } else if (warp >= 4 && warp < 12) {
     // ========================================================== epilogue
-    const int eset = (EPI2 && warp >= 14) ? 1 : 0;      // EPI2: which set = which accumulator stage = tile parity
-    const int q = warp & 3;                             // TMEM lane quarter (fixed by the hardware: warp % 4)
-    const int m = ((eset ? warp - 14 : warp - 4) >> 2); // which 128-row accumulator of the tile
-    const int etq0 = tq0 + eset * tqstep, etqstep = EPI2 ? 2 * tqstep : tqstep;
-    uint32_t acc_it = (uint32_t)eset;
+    const int q = warp & 3;
+    const int m = (warp - 4) >> 2;                      // which 128-row accumulator of the tile
+    uint32_t acc_it = 0;
     // FINAL epilogue: the mean of the input frames (RDN.py:221/279/333) of tile t+1 is loaded while tile t is being
     // processed (one tile of software pipelining: a cold DRAM round trip per tile was the kernel's critical path).
     constexpr int NFV = (EPI == BIN_EPI_FINAL) ? 3 * BIN_MAX_FRAMES : 1;
@@ -439,12 +429,12 @@ __global__ void __launch_bounds__(EPI2 ? kThreads + 64 + 256 : (QUAD ? kThreads 
     constexpr bool kIncr = !PAIR;
     int c_nh = 0, c_tx = 0, c_ty = 0, c_b = 0, d_nh = 0, d_tx = 0, d_ty = 0, d_b = 0;
     if (kIncr && !p.reverse) {
-      int t = etq0;
+      int t = tq0;
       c_nh = t % p.nh; t /= p.nh; c_tx = t % p.tiles_x; t /= p.tiles_x; c_ty = t % p.tiles_y; c_b = t / p.tiles_y;
-      t = etqstep;
+      t = tqstep;
       d_nh = t % p.nh; t /= p.nh; d_tx = t % p.tiles_x; t /= p.tiles_x; d_ty = t % p.tiles_y; d_b = t / p.tiles_y;
     }
-    for (int tq = etq0; tq < tqn; tq += etqstep, acc_it += (EPI2 ? 2u : 1u)) {
+    for (int tq = tq0; tq < tqn; tq += tqstep, ++acc_it) {
       bool live = true;
       int tile, nh, txi, tyi, b;
       if (kIncr && !p.reverse) {
@@ -501,34 +491,10 @@ __global__ void __launch_bounds__(EPI2 ? kThreads + 64 + 256 : (QUAD ? kThreads 
       if (warp == kDbgEpiWarp(p) && lane == 0) dbg_rec(p, 2, acc_it, 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS + m * C::NMMA;
-      bool shifted = false;
-      if constexpr (EPI2) {
-        // x-stack sum in TMEM: column group kx of the finished accumulator is shifted down kx lanes by the tensor pipe
-        // (tcgen05.shift works inside each 32-lane group = one 32-pixel tile row), so the three groups are added lane-wise
-        // below and the 64 SHFL per thread -- which cross the same shared-memory crossbar as the MMA operand fetch, the
-        // resource that bounds this kernel -- disappear.  Issued by one thread per accumulator AFTER tmem_full (a shift is
-        // not ordered behind MMAs to the same columns), its latency is affordable because this set has two tile periods.
-        if (p.shift) {
-          shifted = true;
-          if (q == 0 && elect_one()) {
-            const uint32_t d = tmem_base + as * C::ACC_COLS + m * C::NMMA;
-#pragma unroll
-            for (int kx = 1; kx < 3; ++kx)
-#pragma unroll
-              for (int r = 0; r < kx; ++r)
-#pragma unroll
-                for (int c8 = 0; c8 < NT; c8 += 8) tmem_shift_down(d + kx * NT + c8);
-            umma_commit(&ctrl->shifted[as * 2 + m]);
-          }
-          __syncwarp();
-          mbar_wait(&ctrl->shifted[as * 2 + m], aph, kTag | (5ull << 32) | acc_it);
-          tc_fence_after();
-        }
-      }
       if constexpr (EPI == BIN_EPI_P8) {
         // TMEM loads are issued in batches (tcgen05.wait::ld waits for ALL outstanding loads, so one wait per
         // 16 columns serialised a ~200-cycle round trip six times per tile and made the LFF epilogue the bottleneck)
-        constexpr int GRP = SX ? (EPI2 ? 16 : 32) : (NT % 48 == 0 ? 48 : (NT % 32 == 0 ? 32 : 16));   // output channels per batch
+        constexpr int GRP = SX ? 32 : (NT % 48 == 0 ? 48 : (NT % 32 == 0 ? 32 : 16));   // output channels per batch
 #pragma unroll
         for (int g0 = 0; g0 < NT; g0 += GRP) {
           uint32_t v[(SX ? 3 : 1) * GRP];
@@ -561,8 +527,8 @@ __global__ void __launch_bounds__(EPI2 ? kThreads + 64 + 256 : (QUAD ? kThreads 
               // out[p] = D[p][kx=0] + D[p+1][kx=1] + D[p+2][kx=2]; p+1, p+2 are lanes +1, +2 of this warp
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float b1 = (abl_shfl || shifted) ? __uint_as_float(v[GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[GRP + 16 * j + i]), 1);
-                const float b2 = (abl_shfl || shifted) ? __uint_as_float(v[2 * GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[2 * GRP + 16 * j + i]), 2);
+                const float b1 = abl_shfl ? __uint_as_float(v[GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[GRP + 16 * j + i]), 1);
+                const float b2 = abl_shfl ? __uint_as_float(v[2 * GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[2 * GRP + 16 * j + i]), 2);
                 f[i] = ((__uint_as_float(v[16 * j + i]) + b1) + b2) * kAcc + (abl_bias ? 0.25f : sbias[n0 + i]);
               }
             } else {
@@ -819,7 +785,6 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
   p.msplit = options().msplit ? 1 : 0;
   p.polite = options().polite ? 1 : 0;
   p.spread = options().spread ? 1 : 0;
-  p.shift = options().shift ? 1 : 0;
   p.reverse = (reverse && EPI == BIN_EPI_P8) ? 1 : 0;     // (the FINAL epilogue prefetches tile + gridDim.x: forward only)
 #ifdef BIN_B200_TOOLS
   if (p.debug & 8) {
@@ -853,18 +818,6 @@ static int launch_inst(const bin_conv_args_t& a, cudaStream_t s, bool reverse) {
     // (not with a residual / accumulate epilogue: its prefetch registers do not fit under the 448-thread bound without
     // spills, and the data-gradient convs of the training step measured 1.5 % slower with it)
     if (options().quad && (SX || a.res.ptr == nullptr)) {
-      if constexpr (SX && EPI == BIN_EPI_P8) {
-        if (options().epi2) {
-          auto k2 = conv_igemm_kernel<NT, KS, EPI, SX, X3, false, true, true>;
-          static std::atomic<unsigned long long> epi2_opted{0};
-          BIN_TRY(ensure_dynamic_smem(k2, kSmemMax, epi2_opted));
-          const int g2 = p.ntiles < num_sms() ? p.ntiles : num_sms();
-          if (g2 < 1) return BIN_OK;
-          k2<<<g2, kThreads + 64 + 256, smem_bytes, s>>>(p);
-          BIN_CUDA_OK(cudaGetLastError());
-          return BIN_OK;
-        }
-      }
       auto kq = conv_igemm_kernel<NT, KS, EPI, SX, X3, false, true>;
       static std::atomic<unsigned long long> quad_opted{0};   // per instantiation, per device
       BIN_TRY(ensure_dynamic_smem(kq, kSmemMax, quad_opted));

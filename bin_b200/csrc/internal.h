@@ -52,8 +52,6 @@ struct Options {
   bool msplit;               // BIN_B200_MSPLIT: conv MMA warps split the tile's two accumulators instead of alternating stages
   bool quad;                 // BIN_B200_QUAD=0 falls back to two MMA warps in the x-stacked conv kernel (default: four)
   bool tailq;                // BIN_B200_TAILQ: two MMA warps per tile stream in rdb_tail_kernel (448 threads)
-  bool shift;                // BIN_B200_SHIFT (with EPI2): x-stack sum by tcgen05.shift in TMEM instead of SHFL
-  bool epi2;                 // BIN_B200_EPI2: two alternating sets of epilogue warps in the x-stacked conv (704 threads)
   bool spread;               // BIN_B200_SPREAD: QUAD convs put one MMA warp on each SM sub-partition
   bool polite;               // BIN_B200_POLITE: producers / epilogue warps sleep between barrier polls (power)
   bool zigzag;               // BIN_B200_ZIGZAG: consecutive RDB launches walk the tiles in opposite directions (L2 reuse)
@@ -83,7 +81,7 @@ struct alignas(64) ConvParams {
   int H, W, Btot;                      // conv resolution
   int b0, y0, ny;                      // batch / row sub-range processed by this launch
   int tiles_x, tiles_y, ntiles, nh;    // nh = cout_pad / NT
-  int relu, resident, nstages, cps, debug, msplit, reverse, polite, spread, shift;
+  int relu, resident, nstages, cps, debug, msplit, reverse, polite, spread;
   __half* out; int out_planes, out_plane0, store_planes;
   const __half* res; int res_planes, res_plane0;
   bin_frames_t fr;

@@ -314,16 +314,13 @@ def test_cta_pair_kernels_bit_identical_to_single_cta():
         "print('HASH', h.hexdigest())\n" % ROOT)
     got = {}
     base = {"BIN_B200_PAIR": "0", "BIN_B200_MSPLIT": "0", "BIN_B200_QUAD": "0", "BIN_B200_ZIGZAG": "0", "BIN_B200_TAILQ": "0",
-            "BIN_B200_SPREAD": "0", "BIN_B200_POLITE": "0", "BIN_B200_EPI2": "0", "BIN_B200_SHIFT": "0"}
+            "BIN_B200_SPREAD": "0", "BIN_B200_POLITE": "0"}
     for tag, over in (("two-warp", {}), ("quad", {"BIN_B200_QUAD": "1"}), ("quad+tailq", {"BIN_B200_QUAD": "1", "BIN_B200_TAILQ": "1"}),
                       ("tailq", {"BIN_B200_TAILQ": "1"}), ("pair", {"BIN_B200_PAIR": "1"}),
                       ("msplit", {"BIN_B200_MSPLIT": "1"}), ("pair+msplit", {"BIN_B200_PAIR": "1", "BIN_B200_MSPLIT": "1"}),
                       ("quad+zigzag", {"BIN_B200_QUAD": "1", "BIN_B200_ZIGZAG": "1"}), ("pair+zigzag", {"BIN_B200_PAIR": "1", "BIN_B200_ZIGZAG": "1"}),
                       ("quad+tailq+spread+polite", {"BIN_B200_QUAD": "1", "BIN_B200_TAILQ": "1", "BIN_B200_SPREAD": "1", "BIN_B200_POLITE": "1"}),
-                      ("spread+polite", {"BIN_B200_SPREAD": "1", "BIN_B200_POLITE": "1"}),
-                      ("quad+epi2", {"BIN_B200_QUAD": "1", "BIN_B200_EPI2": "1"}),
-                      ("quad+epi2+shift", {"BIN_B200_QUAD": "1", "BIN_B200_EPI2": "1", "BIN_B200_SHIFT": "1"}),
-                      ("quad+epi2+spread+zigzag", {"BIN_B200_QUAD": "1", "BIN_B200_EPI2": "1", "BIN_B200_SPREAD": "1", "BIN_B200_ZIGZAG": "1"})):
+                      ("spread+polite", {"BIN_B200_SPREAD": "1", "BIN_B200_POLITE": "1"})):
         env = dict(base, **over)
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, (tag, r.stderr[-2000:])
