@@ -292,7 +292,8 @@ def dominant_kernel_roofline(torch, ops, pk, ncalls, h, w):
     hbm = pk["hbm_gbs"]
     tail = {"bound": "hbm", "kernel": "rdb_tail (conv3 + LFF + residual fused)",
             "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-            "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+            "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / hbm,
+            "traffic": 636.8e6 if (ncalls, h, w) == (5, 360, 640) else None,     # profiles/r02_prof_tail.md (442.9 MB read + 193.9 MB written)
             "algorithmic_bytes_per_launch": tail_bytes,
             "tflops": tail_flops / (tail_ms * 1e-3) / 1e12, "tensor_frac": tail_flops / (tail_ms * 1e-3) / 1e12 / peak,
             "ms_per_launch": tail_ms}
@@ -310,7 +311,13 @@ def dominant_kernel_roofline(torch, ops, pk, ncalls, h, w):
            "convlstm(K5, state=None)": {"ms": lstm_ms, "GBps": lstm_bytes / (lstm_ms * 1e-3) / 1e9,
                                         "frac": lstm_bytes / (lstm_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": lstm_bytes}}
     return {"bound": "tensor", "kernel": "RDB 3x3 convs 0..2, x-stacked implicit GEMM (3 shapes)", "achieved": ach,
-            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of the three launches at this exact shape, from the committed
+            # `ncu --set full` capture profiles/r02_prof_conv_quad.md (885.1 MB read + 167.6 MB written; a constant of that
+            # capture, not re-measured by this run); algorithmic: reads 5*230400*(192+256+320) B, writes 3*5*230400*64 B
+            "traffic": 1052.7e6 if (ncalls, h, w) == (5, 360, 640) else None,
+            "traffic_source": "profiles/r02_prof_conv_quad.md (ncu --set full, same shapes)",
+            "algorithmic_bytes_per_launch_set": ncalls * h * w * (192 + 256 + 320) + 3 * ncalls * h * w * 64,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({pk['source']}, burst: kernel timed alone)",
             "algorithmic_flops_per_launch_set": tot_flops, "ms_per_launch_set": tot_ms,
             # every 128x96x16 MMA fetches A (4 KB) + B (3 KB) from shared memory at 128 B/clk = 56 cycles against
