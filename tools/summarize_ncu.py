@@ -29,7 +29,7 @@ def short(name):
     return re.sub(r"\(.*", "", name).replace("binb::", "").replace("void ", "")
 
 
-def launches(csvname="launches_window.csv", outname=None, cmd_note=None):
+def launches(csvname="launches_window.csv", outname=None, cmd_note=None, title="ncu launch list of ONE steady-state 6-frame 1280x720 window"):
     path = os.path.join(G, csvname)
     if not os.path.exists(path):
         return
@@ -46,7 +46,7 @@ def launches(csvname="launches_window.csv", outname=None, cmd_note=None):
         a[1] += v
         tot += v
     with open(os.path.join(P, outname or f"{tag}_launches_window.md"), "w") as f:
-        f.write(f"# {tag}: ncu launch list of ONE steady-state 6-frame 1280x720 window\n\n" +
+        f.write(f"# {tag}: {title}\n\n" +
                 (cmd_note or (f"Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s {528 + len(rows)} -c {len(rows)} --csv python tools/run_window.py 2`\n"
                 f"(BIN_B200_GRAPH=0; skip = 528 weight-pack launches + the {len(rows)} launches of window 0).")) + " Per-launch times under ncu are\n"
                 "cold-cache and serialised: compare SHARES, not absolutes.\n\n"
@@ -101,6 +101,10 @@ if tag == "r01":
          "Algorithmic FLOPs per launch: 2*5*230400*(192*32*9 + 224*96).")
 
 if tag == "r02":
+    launches("r02t_launches_train.csv", "r02_launches_train_step.md",
+             "Command: `BT_STEPS=1 BT_WARM=1 BIN_B200_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/bench_train.py 4 256 256` "
+             "(2 steps: fwd+bwd+loss+Adam, 6-frame net, batch 4 x 256x256; final tree).",
+             title="ncu launch list of a training run (2 optimize_parameters steps)")
     launches("r02z_launches_window.csv", "r02_launches_window.md",
              "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 227 -c 223 --csv python tools/run_window.py 2` "
              "(BIN_B200_GRAPH=0; skip = 4 batched weight-pack launches + the 223 launches of window 0; default switches: four MMA warps, single-CTA kernels; final tree of round 2).")
