@@ -429,6 +429,24 @@ def run_ours(args):
         for _ in range(args.warmup):
             for w_ in wins_dev:
                 net(*w_)
+        # Settle: a box that has been idle (the reference arm runs on the CPU first) starts at the maximum clock and the
+        # power governor then swings below its steady state for a few seconds (seen as a first bench process 6-12 % slower
+        # than every later one on the same box, with `e2e` -- measured later in the same process -- FASTER than the
+        # device-resident value).  Keep running untimed steps for at least 2.5 s and until three consecutive steps agree within
+        # 1.5 % (at most ~6 s); the timed region below is still exactly --steps steps, and what was run here is reported in the line.
+        settle_ms = []
+        t_settle = time.perf_counter()
+        while time.perf_counter() - t_settle < 6.0:
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for w_ in wins_dev:
+                net(*w_)
+            s1.record()
+            s1.synchronize()
+            settle_ms.append(s0.elapsed_time(s1))
+            last = settle_ms[-3:]
+            if time.perf_counter() - t_settle >= 2.5 and max(last) - min(last) <= 0.015 * min(last):
+                break
         barrier()
         sampler.mark_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -464,7 +482,9 @@ def run_ours(args):
     finite = bool(all(torch.isfinite(t).all() for t in outs))
     # per-rank record (the driver computes scaling from `value`; this shows WHICH rank bounds it)
     per_rank = [{"rank": rank, "gpu": local, "ms_per_step": ms_dev / args.steps, "e2e_ms_per_step": ms_e2e / args.steps,
-                 "clocks": clocks}]
+                 "clocks": clocks,
+                 "settle": {"untimed_steps": len(settle_ms), "first_ms": round(settle_ms[0], 2), "last_ms": round(settle_ms[-1], 2),
+                            "slowest_ms": round(max(settle_ms), 2)}}]
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, per_rank[0])
@@ -550,6 +570,7 @@ def run_ours(args):
             "config": {"workload": f"bin_stage4 6-frame window {W}x{H} (SURVEY 8d config 2b; what test.py runs)",
                        "frames": 6, "windows_per_gpu_per_step": S, "outputs": 14,
                        "arithmetic": "fp16 operands / fp32 accumulate (tcgen05 kind::f16), fp32 frames in/out, fp32 ConvLSTM",
+                       "warmup_policy": "--warmup steps, then untimed settle steps (>= 2.5 s, until 3 consecutive steps agree within 1.5 %, <= 6 s; per_rank[].settle) so that the timed steps see the governor's steady state",
                        "l2": f"{S} distinct windows per step, per-window working set (>1 GB of activations per backbone stage) >> 126 MB L2; no explicit flush",
                        "executed_flop_fraction": EXECUTED_FRACTION, "weights": "synthetic U(+-1/sqrt(fan_in)) seed 0",
                        "nccl_init_ms": nccl_init_ms, "weight_broadcast_ms": bcast_ms, "weight_broadcast_bytes": bcast_bytes},
