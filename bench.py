@@ -451,13 +451,18 @@ def run_ours(args):
         sampler.mark_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        marks = []                                   # one event per step boundary (recorded, never waited on in the loop)
         for _ in range(args.steps):
             for w_ in wins_dev:
                 outs = net(*w_)
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
         e1.record()
         barrier()
         sampler.mark_end()
         ms_dev = e0.elapsed_time(e1)
+        step_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
         clocks = sampler.stop()
         # ---- end-to-end: pinned host -> device, forward, 3 result images -> pinned host -----------
         from bin_b200.pipeline import WindowPipeline
@@ -483,6 +488,9 @@ def run_ours(args):
     # per-rank record (the driver computes scaling from `value`; this shows WHICH rank bounds it)
     per_rank = [{"rank": rank, "gpu": local, "ms_per_step": ms_dev / args.steps, "e2e_ms_per_step": ms_e2e / args.steps,
                  "clocks": clocks,
+                 "step_ms": {"min": round(min(step_ms), 2), "median": round(sorted(step_ms)[len(step_ms) // 2], 2),
+                             "max": round(max(step_ms), 2), "first3": [round(x, 2) for x in step_ms[:3]],
+                             "last3": [round(x, 2) for x in step_ms[-3:]]},
                  "settle": {"untimed_steps": len(settle_ms), "first_ms": round(settle_ms[0], 2), "last_ms": round(settle_ms[-1], 2),
                             "slowest_ms": round(max(settle_ms), 2)}}]
     if world > 1:
