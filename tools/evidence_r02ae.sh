@@ -1,10 +1,7 @@
 #!/bin/bash
-# bench.py on a cold box, twice: does the settle phase remove the first-process penalty?
+# bench.py on a cold box, twice: settle phase + per-step times of the timed region
 mkdir -p gpurun_out
 for i in 1 2; do
-  timeout 300 python bench.py --steps 20 --warmup 5 --no-extras 2>/dev/null | python -c "
-import json,sys
-j=json.loads([l for l in sys.stdin.read().strip().split('\n') if l.startswith('{')][-1])
-print('run $i', 'windows/s', round(j['value'],2), 'ms/step', round(j['ms_per_step'],1), 'e2e', round(j['e2e']['value'],2), j['clocks'], j["per_rank"][0]["settle"], j["per_rank"][0]["step_ms"])" >> gpurun_out/r02ag_settle.txt
+  timeout 300 python bench.py --steps 20 --warmup 5 --no-extras > gpurun_out/r02ah_bench_$i.json 2>/dev/null
 done
-cat gpurun_out/r02ag_settle.txt
+python tools/show_bench.py gpurun_out/r02ah_bench_1.json gpurun_out/r02ah_bench_2.json | tee gpurun_out/r02ah_settle.txt
