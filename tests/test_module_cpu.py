@@ -160,3 +160,27 @@ def test_weight_walk_matches_parameters_and_survives_replication(net):
     rw = rep._all_tensors()
     assert len(rw) == 540 and all(torch.equal(a, b * 2.0) for a, b in zip(rw, allt))
     assert rep.model.model1_3 is rep.model.model1_1               # aliases stay aliases inside a replica
+
+
+def test_bench_reference_arm_line_on_cpu():
+    """`bench.py --impl reference` (the driver's reference arm) on a tiny window: one JSON line with the contract's keys,
+    kind "reference" where the unmodified reference is mounted and "port" otherwise; a non-zero rank prints nothing."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--height", "48", "--width", "64",
+           "--steps", "3", "--warmup", "1", "--gpus", "2"]
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().split("\n") if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "720p frame-windows/sec" and j["unit"] == "windows/s"
+    assert j["higher_is_better"] is True and j["value"] > 0 and j["n_gpus"] == 2
+    assert j["steps"] == 2 and j["requested_steps"] == 3            # bounded sample: at most two timed windows
+    cb = j["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
+    assert j["e2e"] == {"value": j["value"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    r1 = subprocess.run(cmd, env=dict(env, RANK="1", LOCAL_RANK="1"), capture_output=True, text=True, timeout=600)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
