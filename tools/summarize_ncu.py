@@ -108,6 +108,9 @@ if tag == "r02":
     launches("r02z_launches_window.csv", "r02_launches_window.md",
              "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 227 -c 223 --csv python tools/run_window.py 2` "
              "(BIN_B200_GRAPH=0; skip = 4 batched weight-pack launches + the 223 launches of window 0; default switches: four MMA warps, single-CTA kernels; final tree of round 2).")
+    PORT = [("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem data pipe: tensor-core operand reads % of peak"),
+            ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem data pipe: LSU (SHFL / LDS / mbarrier) % of peak"),
+            ("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum.pct_of_peak_sustained_elapsed", "  of which shared loads % of peak")]
     FP = [("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe % of peak"),
           ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots active %"),
           ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts")]
@@ -117,9 +120,10 @@ if tag == "r02":
          "convlstm (prev_state=None): 324 FMA + 15 transcendentals per pixel against 36 B -> FP32-FMA bound, not HBM bound (DESIGN 4d).", FP)
     full("r02m_prof_conv_quad.ncu-rep", "ncu --set full: x-stacked RDB convs 0..2 at 5x360x640, final state (four MMA warps, 448 threads)",
          "Command: `ncu --set full --clock-control none --import-source on -k regex:'conv_igemm_kernel<\\(int\\)32' -s 144 -c 3 python tools/run_window.py 2`.\n"
-         "Algorithmic FLOPs per launch: 2*5*230400*(96+32c)*32*9; bytes: reads 5*230400*(192+64c), writes 5*230400*64.")
+         "Algorithmic FLOPs per launch: 2*5*230400*(96+32c)*32*9; bytes: reads 5*230400*(192+64c), writes 5*230400*64.\n"
+         "The two `smem data pipe` rows add up to 90 / 92 / 95 % of the shared-memory data pipe's peak: the kernel is bound by that pipe (DESIGN 4a).", PORT)
     full("r02f_prof_tail.ncu-rep", "ncu --set full: fused RDB tail (default single-CTA kernel) at 5x360x640, final state of round 2",
-         "Command: `ncu --set full --clock-control none --import-source on -k regex:rdb_tail -s 48 -c 1 python tools/run_window.py 2`.")
+         "Command: `ncu --set full --clock-control none --import-source on -k regex:rdb_tail -s 48 -c 1 python tools/run_window.py 2`.", PORT)
     for pr in ("0", "1"):
         full(f"r02f_prof_conv_pair{pr}.ncu-rep", f"ncu --set full: x-stacked RDB convs 0..2 at 5x360x640, BIN_B200_PAIR={pr} ({'CTA-pair cta_group::2' if pr == '1' else 'single-CTA'} kernel), same box",
              f"Command: `BIN_B200_PAIR={pr} ncu --set full --clock-control none --import-source on -k regex:'conv_igemm_kernel<\\(int\\)32' -s 144 -c 3 python tools/run_window.py 2`.\n"
