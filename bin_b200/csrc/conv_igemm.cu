@@ -434,6 +434,13 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
       t = tqstep;
       d_nh = t % p.nh; t /= p.nh; d_tx = t % p.tiles_x; t /= p.tiles_x; d_ty = t % p.tiles_y; d_b = t / p.tiles_y;
     }
+    // x-stacked conv: the 32 biases of the tile's output channels live in registers for the whole persistent loop (they were
+    // 8 LDS.128 per warp and tile on the shared-memory pipe the MMA operands need)
+    float breg[(SX && EPI == BIN_EPI_P8) ? NT : 1];
+    if constexpr (SX && EPI == BIN_EPI_P8) {
+#pragma unroll
+      for (int i = 0; i < NT; ++i) breg[i] = bsrc[i];
+    }
     for (int tq = tq0; tq < tqn; tq += tqstep, ++acc_it) {
       bool live = true;
       int tile, nh, txi, tyi, b;
@@ -529,7 +536,7 @@ __global__ void __launch_bounds__(QUAD ? kThreads + 64 : kThreads, 1) conv_igemm
               for (int i = 0; i < 16; ++i) {
                 const float b1 = abl_shfl ? __uint_as_float(v[GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[GRP + 16 * j + i]), 1);
                 const float b2 = abl_shfl ? __uint_as_float(v[2 * GRP + 16 * j + i]) : __shfl_down_sync(0xffffffffu, __uint_as_float(v[2 * GRP + 16 * j + i]), 2);
-                f[i] = ((__uint_as_float(v[16 * j + i]) + b1) + b2) * kAcc + (abl_bias ? 0.25f : sbias[n0 + i]);
+                f[i] = ((__uint_as_float(v[16 * j + i]) + b1) + b2) * kAcc + (abl_bias ? 0.25f : breg[n0 + i]);
               }
             } else {
 #pragma unroll

@@ -29,7 +29,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         return e0.elapsed_time(e1) / reps
     x = torch.randn(B, 12, h, w, 8, device=dev).half()
     g = torch.randn(B, 16, h, w, 8, device=dev).half()
-    res = {"cfg": {k: os.environ.get(k, "") for k in ("BIN_B200_QUAD", "BIN_B200_MSPLIT", "BIN_B200_STAGE_MMAS", "BIN_B200_PAIR", "BIN_B200_SPREAD", "BIN_B200_DEBUG")}}
+    res = {"cfg": {k: os.environ.get(k, "") for k in ("BIN_B200_QUAD", "BIN_B200_MSPLIT", "BIN_B200_STAGE_MMAS", "BIN_B200_PAIR", "BIN_B200_SPREAD", "BIN_B200_DEBUG", "BIN_B200_LIB")}}
     tot, fl = 0.0, 0.0
     for c in range(3):
         cin = 96 + 32 * c
@@ -65,6 +65,10 @@ else:
         # stores: the kernel with NO HBM traffic is the upper bound of what fusing convs 0..2 (growth maps kept on chip) could save
         tl = os.path.join(ROOT, "bin_b200", "libbin_b200_tools.so")
         cfgs = [{"BIN_B200_LIB": tl, "BIN_B200_DEBUG": d} for d in ("0", "1024", "1280", "0", "1024", "1280")]
+    if len(sys.argv) > 1 and sys.argv[1] == "prevlib":
+        # A/B against a library built from the previous sources (bin_b200/libbin_b200_prev.so, built by hand with the same flags)
+        pl = os.path.join(ROOT, "bin_b200", "libbin_b200_prev.so")
+        cfgs = [{"BIN_B200_LIB": pl}, {}, {"BIN_B200_LIB": pl}, {}]
     if len(sys.argv) > 1 and sys.argv[1] == "spread":
         cfgs = [{"BIN_B200_SPREAD": "0"}, {"BIN_B200_SPREAD": "1"}, {"BIN_B200_SPREAD": "0"}, {"BIN_B200_SPREAD": "1"}]
     for cfg in cfgs:
