@@ -184,3 +184,29 @@ def test_bench_reference_arm_line_on_cpu():
     assert j["e2e"] == {"value": j["value"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     r1 = subprocess.run(cmd, env=dict(env, RANK="1", LOCAL_RANK="1"), capture_output=True, text=True, timeout=600)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_bench_clock_sampler_uses_only_samples_of_the_timed_region():
+    """bench.py's ClockSampler: median / min SM clock and throttle reasons come from the samples that arrived between
+    mark_begin and mark_end (the sampler itself starts before the warm-up); without nvidia-smi it says so."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeProc:
+        def terminate(self):
+            pass
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    row = lambda mhz, cap: ["0", str(mhz), "1965", "700.0", "Not Active", "Not Active", "Not Active", cap]
+    s.rows = [(10.0, row(1965, "Not Active")), (20.5, row(1500, "Active")), (21.0, row(1470, "Active")), (21.5, row(1530, "Active")),
+              (40.0, row(600, "Not Active"))]
+    s.t0, s.t1 = 20.0, 22.0
+    r = s.stop()
+    assert r["sm_mhz"] == 1500 and r["sm_min_mhz"] == 1470 and r["sm_max_mhz"] == 1965 and r["samples"] == 3
+    assert r["reasons"] == ["sw_power_cap"]
+    s2 = bench.ClockSampler(0)                        # nvidia-smi absent (this container)
+    assert s2.stop()["reasons"] == ["nvidia-smi unavailable"]
+    p = bench.peaks()
+    assert p["bf16_tflops"] > 0 and p["hbm_gbs"] > 0 and p["source"] in ("measured", "fallback")
